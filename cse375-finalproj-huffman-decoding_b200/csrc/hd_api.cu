@@ -1,0 +1,391 @@
+// hd_api.cu -- C-ABI entry points (include/hd_b200.h) over the sm_100a kernels.
+// Host orchestration only: workspace carving, launches, the self-sync fixed
+// point loop.  Reference citations are relative to the reference repo root.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "hd_kernels.cuh"
+
+using namespace hd;
+
+namespace {
+
+thread_local cudaError_t g_last_cuda = cudaSuccess;
+
+#define HD_CUDA(call)                              \
+    do {                                           \
+        cudaError_t e__ = (call);                  \
+        if (e__ != cudaSuccess) {                  \
+            g_last_cuda = e__;                     \
+            (void)cudaGetLastError();              \
+            return HD_ERR_CUDA;                    \
+        }                                          \
+    } while (0)
+
+inline uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---- workspace layout -------------------------------------------------------
+// [ctrl A: 64 B {tile_counter u32}] [tile_status: n_tiles u64]   <- zeroed per K4 launch
+// [ctrl B: 64 B {changed[8] u32, count u64}]                      <- zeroed per self-sync call
+// [gap words (self-sync only): n_chunks u32]
+// [blk_entry (self-sync only): n_sync_blocks u8]
+struct Workspace {
+    uint32_t *tile_counter;
+    uint64_t *tile_status;
+    uint32_t *changed;       // 8 counters
+    uint64_t *count;
+    uint32_t *gap_words;
+    uint8_t *blk_entry;
+    size_t zero_bytes;       // prefix of the workspace that must be zeroed per K4 launch
+};
+
+constexpr size_t kCtrlBytes = 64;
+
+size_t ws_bytes(uint64_t n_units, bool selfsync) {
+    const uint64_t n_seg = div_up(n_units, kSegmentUnits);
+    const uint64_t n_tiles = std::max<uint64_t>(1, div_up(n_seg, kTileThreads));
+    size_t b = kCtrlBytes + align_up(n_tiles * 8, 64) + kCtrlBytes;
+    if (selfsync) {
+        const uint64_t n_chunks = std::max<uint64_t>(1, div_up(n_seg, kChunkSegs));
+        const uint64_t n_blocks = div_up(n_chunks, kSyncThreads);
+        b += align_up(n_chunks * 4, 64) + align_up(n_blocks, 64);
+    }
+    return b;
+}
+
+Workspace carve(void *ws, uint64_t n_units, bool selfsync) {
+    Workspace w;
+    uint8_t *p = static_cast<uint8_t *>(ws);
+    const uint64_t n_seg = div_up(n_units, kSegmentUnits);
+    const uint64_t n_tiles = std::max<uint64_t>(1, div_up(n_seg, kTileThreads));
+    w.tile_counter = reinterpret_cast<uint32_t *>(p);
+    w.tile_status = reinterpret_cast<uint64_t *>(p + kCtrlBytes);
+    w.zero_bytes = kCtrlBytes + align_up(n_tiles * 8, 64);
+    uint8_t *b = p + w.zero_bytes;
+    w.changed = reinterpret_cast<uint32_t *>(b);
+    w.count = reinterpret_cast<uint64_t *>(b + 48);
+    w.gap_words = nullptr;
+    w.blk_entry = nullptr;
+    if (selfsync) {
+        const uint64_t n_chunks = std::max<uint64_t>(1, div_up(n_seg, kChunkSegs));
+        w.gap_words = reinterpret_cast<uint32_t *>(b + kCtrlBytes);
+        w.blk_entry = b + kCtrlBytes + align_up(n_chunks * 4, 64);
+    }
+    return w;
+}
+
+TableDev table_dev(const hd_table *t) {
+    TableDev d;
+    d.blob = t->d_blob;
+    d.lut_bits = t->host.lut_bits;
+    d.has_long = t->host.has_long;
+    d.off_sync = t->host.off_sync;
+    d.off_len = t->host.off_len;
+    d.off_order = t->host.off_order;
+    d.off_long = t->host.off_long;
+    return d;
+}
+
+struct DeviceInfo {
+    int sm_count = 0;
+    int max_smem_optin = 0;
+};
+DeviceInfo device_info() {
+    static std::mutex mu;
+    static DeviceInfo cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && cache[dev].sm_count) return cache[dev];
+    DeviceInfo d;
+    cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (dev >= 0 && dev < 64) cache[dev] = d;
+    return d;
+}
+
+size_t decode_smem_bytes(const hd_table *t, uint32_t &stage_words, uint32_t &tile_bytes) {
+    const uint32_t min_len = std::max<uint32_t>(1, t->host.min_len);
+    const uint32_t max_sym = (kSegmentBits + min_len - 1) / min_len;   // symbols starting inside one segment
+    stage_words = (max_sym + 1) / 4 + 2;
+    tile_bytes = (uint32_t)align_up((size_t)kTileThreads * max_sym + 32, 16);
+    return (4u << t->host.lut_bits) + 512 + align_up(sizeof(LongTables), 16) +
+           (size_t)stage_words * kTileThreads * 4 + tile_bytes;
+}
+
+size_t sync_smem_bytes(const hd_table *t) {
+    return align_up(2u << t->host.lut_bits, 16) + 256 + align_up(sizeof(LongTables), 16);
+}
+
+template <bool LONG>
+hd_status launch_decode(const DecodeParams &p, size_t smem, cudaStream_t s) {
+    auto kern = hd_decode_write_kernel<LONG>;
+    HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    HD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem));
+    if (per_sm < 1) return HD_ERR_INVALID;
+    const DeviceInfo di = device_info();
+    uint64_t grid = (uint64_t)di.sm_count * per_sm;   // persistent: one wave, a multiple of the SM count
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    kern<<<(unsigned)grid, kTileThreads, smem, s>>>(p);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32_t *d_gap_words,
+                         uint64_t n_segments, uint32_t first_bit, const hd_table *table, uint8_t *d_out,
+                         uint64_t n_symbols, const Workspace &w, uint64_t *d_count, cudaStream_t s) {
+    DecodeParams p;
+    p.units = d_units;
+    p.n_units = n_units;
+    p.gap_words = d_gap_words;
+    p.n_segments = n_segments;
+    p.first_bit = first_bit;
+    p.table = table_dev(table);
+    p.out = d_out;
+    p.n_symbols = n_symbols;
+    p.tile_status = w.tile_status;
+    p.tile_counter = w.tile_counter;
+    p.n_tiles = div_up(n_segments, kTileThreads);
+    p.count_out = d_count;
+    const size_t smem = decode_smem_bytes(table, p.stage_words, p.tile_bytes);
+    if ((int)smem > device_info().max_smem_optin) return HD_ERR_INVALID;
+    HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes, s));
+    return table->host.has_long ? launch_decode<true>(p, smem, s) : launch_decode<false>(p, smem, s);
+}
+
+hd_status check_common(const uint32_t *d_units, uint64_t n_units, const hd_table *table, const uint8_t *d_out,
+                       uint64_t n_symbols, const void *ws) {
+    if (!table || !table->d_blob) return HD_ERR_INVALID;
+    if (n_units == 0) return n_symbols == 0 ? HD_OK : HD_ERR_INVALID;
+    if (!d_units || (!d_out && n_symbols) || !ws) return HD_ERR_INVALID;
+    if (reinterpret_cast<uintptr_t>(d_units) & 15u) return HD_ERR_INVALID;   // 128-bit segment loads
+    if (reinterpret_cast<uintptr_t>(ws) & 63u) return HD_ERR_INVALID;
+    return HD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *hd_version(void) { return "hd_b200 0.1 (sm_100a)"; }
+
+const char *hd_status_string(hd_status s) {
+    switch (s) {
+        case HD_OK: return "ok";
+        case HD_ERR_INVALID: return "invalid argument";
+        case HD_ERR_CUDA: return "CUDA error";
+        case HD_ERR_WORKSPACE: return "workspace too small";
+        case HD_ERR_FORMAT: return "malformed input";
+        case HD_ERR_UNRESOLVED: return "self-synchronisation did not converge";
+    }
+    return "unknown";
+}
+
+const char *hd_last_cuda_error(void) { return cudaGetErrorString(g_last_cuda); }
+
+// ---------------------------------------------------------------- tables
+static hd_status upload_table(const HostCode &c, void *stream, hd_table **out) {
+    hd_table *t = new (std::nothrow) hd_table();
+    if (!t) return HD_ERR_INVALID;
+    build_table_blob(c, t->host);
+    cudaError_t e = cudaGetDevice(&t->device);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&t->d_blob), t->host.total_bytes);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(t->d_blob, t->host.bytes.data(), t->host.total_bytes, cudaMemcpyHostToDevice,
+                            static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) {
+        g_last_cuda = e;
+        (void)cudaGetLastError();
+        if (t->d_blob) cudaFree(t->d_blob);
+        delete t;
+        return HD_ERR_CUDA;
+    }
+    *out = t;
+    return HD_OK;
+}
+
+hd_status hd_table_from_flat_lut(const hd_lut_entry *lut, uint32_t lut_bits, void *stream, hd_table **out) {
+    if (!out) return HD_ERR_INVALID;
+    HostCode c;
+    if (!code_from_flat_lut(lut, lut_bits, c)) return HD_ERR_FORMAT;
+    return upload_table(c, stream, out);
+}
+
+hd_status hd_table_from_lengths(const hd_sym_len *pairs, uint32_t n_pairs, void *stream, hd_table **out) {
+    if (!out) return HD_ERR_INVALID;
+    HostCode c;
+    if (!code_from_pairs(pairs, n_pairs, c)) return HD_ERR_FORMAT;
+    return upload_table(c, stream, out);
+}
+
+void hd_table_free(hd_table *t) {
+    if (!t) return;
+    if (t->d_blob) cudaFree(t->d_blob);
+    delete t;
+}
+
+uint32_t hd_table_max_length(const hd_table *t) { return t ? t->host.max_len : 0; }
+uint32_t hd_table_min_length(const hd_table *t) { return t ? t->host.min_len : 0; }
+
+// ------------------------------------------------------------- workspace
+size_t hd_workspace_bytes_gap(uint64_t n_units) { return ws_bytes(n_units, false); }
+size_t hd_workspace_bytes_selfsync(uint64_t n_units) { return ws_bytes(n_units, true); }
+
+// ---------------------------------------------------------------- decode
+hd_status hd_decode_gap_ex(const uint32_t *d_units, uint64_t n_units, const uint32_t *d_gap_words,
+                           uint64_t n_segments, uint32_t first_bit, const hd_table *table, uint8_t *d_out,
+                           uint64_t n_symbols, void *d_workspace, size_t workspace_bytes, uint64_t *d_count,
+                           void *stream) {
+    hd_status st = check_common(d_units, n_units, table, d_out, n_symbols, d_workspace);
+    if (st != HD_OK) return st;
+    if (n_units == 0) return HD_OK;
+    if (n_segments != div_up(n_units, kSegmentUnits) || first_bit > 15) return HD_ERR_INVALID;
+    if (n_segments > 1 && !d_gap_words) return HD_ERR_INVALID;
+    if (workspace_bytes < ws_bytes(n_units, false)) return HD_ERR_WORKSPACE;
+    Workspace w = carve(d_workspace, n_units, false);
+    return run_gap_decode(d_units, n_units, d_gap_words, n_segments, first_bit, table, d_out, n_symbols, w,
+                          d_count, static_cast<cudaStream_t>(stream));
+}
+
+hd_status hd_decode_gap(const uint32_t *d_units, uint64_t n_units, const uint32_t *d_gap_words,
+                        uint64_t n_segments, const hd_table *table, uint8_t *d_out, uint64_t n_symbols,
+                        void *d_workspace, size_t workspace_bytes, void *stream) {
+    return hd_decode_gap_ex(d_units, n_units, d_gap_words, n_segments, 0, table, d_out, n_symbols, d_workspace,
+                            workspace_bytes, nullptr, stream);
+}
+
+// phases 1+2: build the gap array of a stream by self-synchronisation
+static hd_status run_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit, const hd_table *table,
+                          uint32_t *d_gap_words, uint8_t *d_blk_entry, uint32_t *d_changed, cudaStream_t s) {
+    SyncParams p;
+    p.units = d_units;
+    p.n_units = n_units;
+    p.n_segments = div_up(n_units, kSegmentUnits);
+    p.n_chunks = div_up(p.n_segments, kChunkSegs);
+    p.n_blocks = div_up(p.n_chunks, kSyncThreads);
+    p.first_bit = first_bit;
+    p.table = table_dev(table);
+    p.gap_words = d_gap_words;
+    p.blk_entry = d_blk_entry;
+    p.changed = d_changed;
+    const size_t smem = sync_smem_bytes(table);
+    HD_CUDA(cudaFuncSetAttribute(hd_sync_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HD_CUDA(cudaFuncSetAttribute(hd_sync_seams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hd_sync_chunks_kernel<<<(unsigned)p.n_blocks, kSyncThreads, smem, s>>>(p);
+    HD_CUDA(cudaGetLastError());
+    if (p.n_blocks > 1) {
+        // two seam rounds up front: the first repairs the heads of the blocks,
+        // the second only verifies (changed[1] == 0 <=> fixed point reached)
+        const unsigned grid = (unsigned)div_up(p.n_blocks - 1, kSyncThreads);
+        for (int round = 0; round < 2; ++round) {
+            p.changed = d_changed + round;
+            hd_sync_seams_kernel<<<grid, kSyncThreads, smem, s>>>(p);
+            HD_CUDA(cudaGetLastError());
+        }
+    }
+    return HD_OK;
+}
+
+// further seam rounds until no block exit changes (host loop of the reference:
+// cuhd_gpu_decoder.cu:461-495); only reached for codes that fail to
+// synchronise inside a whole 128-chunk block.
+static hd_status finish_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit, const hd_table *table,
+                             uint32_t *d_gap_words, uint8_t *d_blk_entry, uint32_t *d_changed, cudaStream_t s,
+                             bool *extra_rounds) {
+    *extra_rounds = false;
+    const uint64_t n_segments = div_up(n_units, kSegmentUnits);
+    const uint64_t n_chunks = div_up(n_segments, kChunkSegs);
+    const uint64_t n_blocks = div_up(n_chunks, kSyncThreads);
+    if (n_blocks <= 1) return HD_OK;
+    uint32_t h_changed = 0;
+    HD_CUDA(cudaMemcpyAsync(&h_changed, d_changed + 1, 4, cudaMemcpyDeviceToHost, s));
+    HD_CUDA(cudaStreamSynchronize(s));
+    if (h_changed == 0) return HD_OK;
+    *extra_rounds = true;
+    SyncParams p;
+    p.units = d_units;
+    p.n_units = n_units;
+    p.n_segments = n_segments;
+    p.n_chunks = n_chunks;
+    p.n_blocks = n_blocks;
+    p.first_bit = first_bit;
+    p.table = table_dev(table);
+    p.gap_words = d_gap_words;
+    p.blk_entry = d_blk_entry;
+    p.changed = d_changed + 2;
+    const size_t smem = sync_smem_bytes(table);
+    const unsigned grid = (unsigned)div_up(n_blocks - 1, kSyncThreads);
+    for (uint64_t round = 0; round <= n_blocks; ++round) {
+        HD_CUDA(cudaMemsetAsync(p.changed, 0, 4, s));
+        hd_sync_seams_kernel<<<grid, kSyncThreads, smem, s>>>(p);
+        HD_CUDA(cudaGetLastError());
+        HD_CUDA(cudaMemcpyAsync(&h_changed, p.changed, 4, cudaMemcpyDeviceToHost, s));
+        HD_CUDA(cudaStreamSynchronize(s));
+        if (h_changed == 0) return HD_OK;
+    }
+    return HD_ERR_UNRESOLVED;
+}
+
+hd_status hd_selfsync_gap_array(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit,
+                                const hd_table *table, uint32_t *d_gap_words_out, void *d_workspace,
+                                size_t workspace_bytes, void *stream) {
+    hd_status st = check_common(d_units, n_units, table, nullptr, 0, d_workspace);
+    if (st != HD_OK) return st;
+    if (n_units == 0) return HD_OK;
+    if (!d_gap_words_out || first_bit > 15) return HD_ERR_INVALID;
+    if (workspace_bytes < ws_bytes(n_units, true)) return HD_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Workspace w = carve(d_workspace, n_units, true);
+    HD_CUDA(cudaMemsetAsync(w.changed, 0, kCtrlBytes, s));
+    st = run_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, s);
+    if (st != HD_OK) return st;
+    bool extra = false;
+    st = finish_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, s, &extra);
+    if (st != HD_OK) return st;
+    const uint64_t n_seg = div_up(n_units, kSegmentUnits);
+    // chunk words are exactly the .huff gap words (8 nibbles each); the last
+    // word may describe segments past the end, which is harmless
+    HD_CUDA(cudaMemcpyAsync(d_gap_words_out, w.gap_words, div_up(n_seg, 8) * 4, cudaMemcpyDeviceToDevice, s));
+    return HD_OK;
+}
+
+hd_status hd_decode_selfsync_ex(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit,
+                                const hd_table *table, uint8_t *d_out, uint64_t n_symbols, void *d_workspace,
+                                size_t workspace_bytes, uint64_t *d_count, void *stream) {
+    hd_status st = check_common(d_units, n_units, table, d_out, n_symbols, d_workspace);
+    if (st != HD_OK) return st;
+    if (n_units == 0) return HD_OK;
+    if (first_bit > 15) return HD_ERR_INVALID;
+    if (workspace_bytes < ws_bytes(n_units, true)) return HD_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Workspace w = carve(d_workspace, n_units, true);
+    const uint64_t n_seg = div_up(n_units, kSegmentUnits);
+    // K1a + K1b x2, then K4 speculatively; the convergence flag is read once at
+    // the end (the reference reads flags after every phase-2 launch, :461-495)
+    HD_CUDA(cudaMemsetAsync(w.changed, 0, kCtrlBytes, s));
+    st = run_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, s);
+    if (st != HD_OK) return st;
+    st = run_gap_decode(d_units, n_units, w.gap_words, n_seg, first_bit, table, d_out, n_symbols, w, d_count, s);
+    if (st != HD_OK) return st;
+    bool extra = false;
+    st = finish_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, s, &extra);
+    if (st != HD_OK) return st;
+    if (extra)   // the speculative K4 ran on an unconverged gap array: redo it
+        st = run_gap_decode(d_units, n_units, w.gap_words, n_seg, first_bit, table, d_out, n_symbols, w, d_count, s);
+    return st;
+}
+
+hd_status hd_decode_selfsync(const uint32_t *d_units, uint64_t n_units, const hd_table *table, uint8_t *d_out,
+                             uint64_t n_symbols, void *d_workspace, size_t workspace_bytes, void *stream) {
+    return hd_decode_selfsync_ex(d_units, n_units, 0, table, d_out, n_symbols, d_workspace, workspace_bytes,
+                                 nullptr, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+// hd_core.h -- per-thread building blocks of the decode kernels, written as
+// host/device inline functions so that the SAME source can be single-stepped by
+// the CPU emulator under tests/emul (test infrastructure; the product library
+// only ever runs them inside the CUDA kernels of hd_kernels.cuh).
+#ifndef HD_CORE_H_
+#define HD_CORE_H_
+
+#include <stdint.h>
+
+#include "hd_internal.h"
+
+#if defined(__CUDACC__)
+#define HD_HD __host__ __device__ __forceinline__
+#else
+#define HD_HD inline
+#endif
+
+namespace hd {
+
+// upper 32 bits of (hi:lo) << (s & 31)
+HD_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    s &= 31u;
+    return s ? ((hi << s) | (lo >> (32u - s))) : hi;
+#endif
+}
+
+// Canonical resolver for codes longer than the primary LUT (len in
+// (lut_bits, 16]).  win = next 32 stream bits, left aligned.  Returns a
+// synthesized primary entry {sym, 0, bits=len, count=1}, or a 1-bit skip for a
+// window that matches no code (hole of an incomplete code).
+HD_HD uint32_t resolve_long(uint32_t win, uint32_t lut_bits, const LongTables *lt, const uint8_t *order) {
+    for (uint32_t len = lut_bits + 1; len <= kMaxCodeLen; ++len) {
+        const uint32_t c = win >> (32 - len);
+        const uint32_t d = c - lt->first[len];
+        if (d < lt->count[len]) return (uint32_t)order[lt->offset[len] + d] | (len << 16) | (1u << 24);
+    }
+    return 1u << 16;
+}
+
+struct DecodeTables {
+    const uint32_t *lut;     // primary multi-symbol LUT {sym0, sym1, bits, count}
+    uint32_t idx_shift;      // 32 - lut_bits
+    uint32_t lut_bits;
+    const uint8_t *len_tab;  // code length by symbol
+    const LongTables *lt;
+    const uint8_t *order;
+};
+
+// Decode one 128-bit segment held in r0..r3 (+ r4 = first unit of the next
+// segment) starting at bit `start` (0..15).  Symbols are appended to the
+// thread's private staging words st[0], st[stride], st[2*stride], ...
+// (little-endian bytes).  Returns the number of symbols whose codeword STARTS
+// inside the segment (the stop rule of decoder.cu:672: start bit < 128).
+//
+// State word S = bit position | symbol count << 8 so that one add of the LUT
+// entry's upper half advances both; bit 7 of S = "position >= 128", bit 5
+// flips when a 32-bit unit boundary is crossed (window refill), bit 10 flips
+// when the pending output word fills up.
+template <bool LONG>
+HD_HD uint32_t decode_segment(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t start,
+                              const DecodeTables &T, uint32_t *st, uint32_t stride) {
+    uint32_t S = start;
+    uint32_t acc = 0;
+    uint32_t e;
+    do {
+        const uint32_t win = funnel_l(r1, r0, S);   // next 32 stream bits
+        e = T.lut[win >> T.idx_shift];
+        if (LONG) {
+            if ((e >> 16) == 0) e = resolve_long(win, T.lut_bits, T.lt, T.order);
+        }
+        const uint32_t Sn = S + (e >> 16);
+        const uint32_t sh = (S >> 5) & 24u;   // 8 * (count & 3)
+        const uint32_t sy = e & 0xffffu;
+        const uint32_t lo = acc | (sy << sh);
+        const uint32_t hi = funnel_l(sy, 0u, sh);   // sy >> (32 - sh), 0 when sh == 0
+        const uint32_t x = Sn ^ S;
+        const bool full = (x & 0x400u) != 0;
+        if (full) { *st = lo; st += stride; }
+        acc = full ? hi : lo;
+        if (x & 32u) { r0 = r1; r1 = r2; r2 = r3; r3 = r4; }
+        S = Sn;
+    } while (!(S & 0x80u));
+    // a second symbol of the last lookup that starts at/after bit 128 belongs to
+    // the next segment
+    if ((e >> 24) == 2) {
+        const uint32_t len1 = T.len_tab[(e >> 8) & 0xffu];
+        if ((S & 0xffu) - len1 >= kSegmentBits) S -= 0x100u;
+    }
+    *st = acc;
+    return S >> 8;
+}
+
+// Copy c symbols from the thread's staging words (src[0], src[stride], ...) to
+// byte offset D of the CTA's output tile.  Interior words are written as whole
+// 32-bit stores, the (at most two) words shared with neighbouring threads byte
+// by byte.
+HD_HD void compact_to_tile(const uint32_t *src, uint32_t stride, uint32_t c, uint8_t *tile, uint32_t D) {
+    const uint32_t delta = D & 3u;
+    const uint32_t sh = delta * 8u;
+    const uint32_t D0 = D & ~3u;
+    uint32_t *dst32 = reinterpret_cast<uint32_t *>(tile + D0);
+    const uint32_t total = delta + c;
+    const uint32_t nw = (total + 3u) >> 2;
+    uint32_t prev = 0;
+    for (uint32_t m = 0; m < nw; ++m) {
+        const uint32_t cur = src[(size_t)m * stride];
+        const uint32_t v = funnel_l(prev, cur, sh);
+        prev = cur;
+        const uint32_t lo_b = (m == 0) ? delta : 0u;
+        const uint32_t rem = total - 4u * m;
+        const uint32_t hi_b = rem < 4u ? rem : 4u;
+        if (lo_b == 0 && hi_b == 4) {
+            dst32[m] = v;
+        } else {
+            uint8_t *d8 = tile + D0 + 4u * m;
+            for (uint32_t b = lo_b; b < hi_b; ++b) d8[b] = (uint8_t)(v >> (8u * b));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- sync side
+struct SyncLut {
+    const uint16_t *lut;   // {jump_bits | first_len << 8}
+    uint32_t idx_shift;
+    uint32_t lm;
+    const LongTables *lt;
+    const uint8_t *order;
+    bool has_long;
+};
+
+struct Seg4 {
+    uint32_t x, y, z, w;
+};
+
+// Parse chunk `chunk` (kChunkSegs segments) starting at bit offset `entry` of
+// its first segment and record, in nibble k of the returned word, the offset at
+// which the parse enters segment 8*chunk+k+1.  With check=true the parse stops
+// as soon as such an offset equals the one already recorded in `word`: the two
+// parses have merged and are identical from there on (the reference tests the
+// same condition, cuhd_gpu_decoder.cu:208-213).  LoadSeg(s) returns the four
+// units of segment s (zeros past the end of the stream).
+template <typename LoadSeg>
+HD_HD uint32_t sync_parse_chunk(LoadSeg load_seg, uint64_t chunk, uint32_t entry, const SyncLut &L, bool check,
+                                uint32_t word, bool &merged) {
+    const uint64_t seg0 = chunk * kChunkSegs;
+    Seg4 cur = load_seg(seg0);
+    Seg4 nxt = load_seg(seg0 + 1);
+    uint32_t off = entry;
+    merged = false;
+    for (uint32_t k = 0; k < kChunkSegs; ++k) {
+        uint32_t r0 = cur.x, r1 = cur.y, r2 = cur.z, r3 = cur.w, r4 = nxt.x;
+        uint32_t pos = off;
+        do {
+            const uint32_t win = funnel_l(r1, r0, pos);
+            uint32_t ent = L.lut[win >> L.idx_shift];
+            uint32_t first = ent >> 8;
+            if (L.has_long && first == 0) {
+                first = (resolve_long(win, L.lm, L.lt, L.order) >> 16) & 0xffu;
+                ent = first | (first << 8);
+            }
+            const uint32_t jump = ent & 0xffu;
+            // a multi-code jump is only safe while it cannot pass the segment end
+            const uint32_t step = (pos + jump <= kSegmentBits) ? jump : first;
+            const uint32_t np = pos + step;
+            if ((np ^ pos) & 32u) { r0 = r1; r1 = r2; r2 = r3; r3 = r4; }
+            pos = np;
+        } while (pos < kSegmentBits);
+        off = pos - kSegmentBits;
+        const uint32_t shift = 4u * k;
+        if (check && ((word >> shift) & 15u) == off) { merged = true; break; }
+        word = (word & ~(15u << shift)) | (off << shift);
+        cur = nxt;
+        nxt = load_seg(seg0 + k + 2);
+    }
+    return word;
+}
+
+}  // namespace hd
+#endif  // HD_CORE_H_

@@ -1,0 +1,72 @@
+// hd_internal.h -- shared declarations between the host side (tables, formats,
+// encoder) and the CUDA side (kernels + C-ABI entry points).  Not installed.
+#ifndef HD_INTERNAL_H_
+#define HD_INTERNAL_H_
+
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "hd_b200.h"
+
+namespace hd {
+
+// ---- geometry of the decode-and-write kernel (K4) -------------------------
+constexpr uint32_t kSegmentBits = 128;   // .huff SEGMENTSIZE (encoder/include/constants.hpp:12)
+constexpr uint32_t kSegmentUnits = 4;    // gpuhd SUBSEQ_SIZE (gpuhd/src/demo.cc:16)
+constexpr uint32_t kTileThreads = 256;   // segments per tile (one per thread)
+constexpr uint32_t kMaxLutBits = 12;     // primary multi-symbol LUT index width
+constexpr uint32_t kMaxCodeLen = 16;     // .huff MAX_CODEWORD_LENGTH (decoder/include/constants.hpp:5)
+
+// ---- geometry of the synchronisation kernels (K1a/K1b) --------------------
+constexpr uint32_t kChunkSegs = 8;       // segments per sync thread (= one gap word)
+constexpr uint32_t kSyncThreads = 128;   // chunks per sync block
+
+// Host description of a prefix code: code/len indexed by symbol value.
+struct HostCode {
+    uint32_t code[256];
+    uint8_t len[256];
+    uint32_t n_present = 0;
+    uint32_t min_len = 0;
+    uint32_t max_len = 0;
+    // symbols in canonical order (non-decreasing length, then increasing code)
+    uint8_t order[256];
+};
+
+bool code_from_flat_lut(const hd_lut_entry *lut, uint32_t lut_bits, HostCode &c);
+bool code_from_pairs(const hd_sym_len *pairs, uint32_t n, HostCode &c);
+
+// Long-code (len > lut_bits) resolver tables, canonical first-code form.
+struct LongTables {
+    uint32_t first[17];   // first code of each length (right aligned)
+    uint32_t count[17];   // number of codes of each length
+    uint32_t offset[17];  // index of first symbol of each length in `order`
+};
+
+// All tables the kernels consume, laid out in ONE device blob:
+//   [0]                      u32 dec_lut[1<<lut_bits]   {sym0,sym1,bits|count<<8}
+//   [off_sync]               u16 sync_lut[1<<lut_bits]  {jump_bits, first_len}
+//   [off_len]                u8  len_tab[256]
+//   [off_order]              u8  order[256]
+//   [off_long]               LongTables
+struct TableBlob {
+    uint32_t lut_bits = 0;
+    uint32_t min_len = 0, max_len = 0;
+    uint32_t has_long = 0;
+    uint32_t off_sync = 0, off_len = 0, off_order = 0, off_long = 0;
+    uint32_t total_bytes = 0;
+    std::vector<uint8_t> bytes;
+};
+
+void build_table_blob(const HostCode &c, TableBlob &blob);
+
+}  // namespace hd
+
+// The opaque handle of the C ABI.
+struct hd_table {
+    hd::TableBlob host;
+    uint8_t *d_blob = nullptr;
+    int device = -1;
+};
+
+#endif  // HD_INTERNAL_H_

@@ -1,0 +1,211 @@
+/*
+ * hd_b200.h -- C ABI of the B200-native (sm_100a) parallel Huffman decoder.
+ *
+ * Drop-in boundary for ONE hot path of dek226/CSE375-FinalProj-Huffman-Decoding:
+ * decoding a canonical Huffman bitstream in parallel through
+ *   (a) the self-synchronisation scheme  (gpuhd/src/cuhd_gpu_decoder.cu) and
+ *   (b) the gap-array scheme  (Huffman_coding_Gap_arrays/decoder/src/decoder.cu).
+ * Plain pointers and sizes only; no C++/torch types.  Every entry point cites
+ * the reference interface it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *  - "units" are host-endian uint32 words, bit 31 of unit 0 is the first code
+ *    bit (gpuhd/encoder/src/llhuffman_encoder.cc:216-231,
+ *    Huffman_coding_Gap_arrays/encoder/src/encoder.cu:295-331).
+ *  - d_* pointers are device pointers on the current CUDA device; `stream` is a
+ *    cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - All functions return hd_status instead of the reference's print-and-exit
+ *    (gpuhd/include/cuhd_cuda_definitions.h:21-28, decoder.cu:14-20); the C++
+ *    shim classes keep exit(1) for the demos.
+ *  - No CPU fallback exists: without a CUDA device every compute call returns
+ *    HD_ERR_CUDA.
+ */
+#ifndef HD_B200_H_
+#define HD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    HD_OK = 0,
+    HD_ERR_INVALID = 1,     /* bad argument */
+    HD_ERR_CUDA = 2,        /* CUDA runtime error (see hd_last_cuda_error) */
+    HD_ERR_WORKSPACE = 3,   /* workspace too small */
+    HD_ERR_FORMAT = 4,      /* malformed .huff image / code table */
+    HD_ERR_UNRESOLVED = 5   /* self-sync fixed point not reached (internal) */
+} hd_status;
+
+/* == cuhd::CUHDCodetableItemSingle  (gpuhd/include/cuhd_codetable.h:20-23) */
+typedef struct {
+    uint8_t num_bits;
+    uint8_t symbol;
+} hd_lut_entry;
+
+/* one {symbol,length} pair of a .huff header
+ * (Huffman_coding_Gap_arrays/encoder/src/huff.cpp:189-194) */
+typedef struct {
+    uint8_t symbol;
+    uint8_t length;
+} hd_sym_len;
+
+const char *hd_version(void);
+const char *hd_status_string(hd_status s);
+/* last cudaError_t seen by this library on the calling thread, as text */
+const char *hd_last_cuda_error(void);
+
+/* ------------------------------------------------------------------ tables
+ * Device-resident decode tables.  Replaces cuhd::CUHDGPUCodetable
+ * (gpuhd/include/cuhd_gpu_codetable.h, allocate + cpy_host_to_device) and the
+ * two-level table of get_table_info/get_twolevel_table
+ * (Huffman_coding_Gap_arrays/decoder/src/get_table.cpp:3-139). */
+typedef struct hd_table hd_table;
+
+/* From the reference's flat LUT: 2^lut_bits x {num_bits,symbol}, index = next
+ * lut_bits stream bits (gpuhd/encoder/src/llhuffman_encoder.cc:240-262).
+ * lut_bits <= 16. */
+hd_status hd_table_from_flat_lut(const hd_lut_entry *lut, uint32_t lut_bits,
+                                 void *stream, hd_table **out);
+/* From a .huff header list in file order (non-decreasing length, canonical
+ * codes by code=(code+1)<<(next_len-len); decoder/src/get_table.cpp:17-20).
+ * Lengths 1..16. */
+hd_status hd_table_from_lengths(const hd_sym_len *pairs, uint32_t n_pairs,
+                                void *stream, hd_table **out);
+void hd_table_free(hd_table *t);
+uint32_t hd_table_max_length(const hd_table *t);
+uint32_t hd_table_min_length(const hd_table *t);
+
+/* --------------------------------------------------------------- workspace
+ * Replaces cuhd::CUHDGPUDecoderMemory (gpuhd/src/cuhd_gpu_decoder_memory.cc:
+ * 25-48: 16 B sync point + 4 B count per subsequence + flags) and the
+ * per-segment output_pos array of decoder.cu:754.  Ours: 8 B per tile of 256
+ * segments + (self-sync) 4 bits per 128-bit subsequence. */
+size_t hd_workspace_bytes_gap(uint64_t n_units);
+size_t hd_workspace_bytes_selfsync(uint64_t n_units);
+
+/* ------------------------------------------------------------------ decode
+ * Gap-array scheme.  Replaces gpu_dec_l1_l2 + decoder_l1_l2
+ * (Huffman_coding_Gap_arrays/decoder/src/decoder.cu:454-730, 732-815;
+ * declared decoder/include/decoder.cuh:4-15).  d_gap_words: ceil(n_segments/8)
+ * words, element i in word i/8 bits [4(i%8),4(i%8)+3]; segment k>0 starts at
+ * bit 128k+gap[k-1] (decoder.cu:505-507).  Writes exactly n_symbols bytes
+ * (fewer only if the stream holds fewer codewords).  Asynchronous on stream. */
+hd_status hd_decode_gap(const uint32_t *d_units, uint64_t n_units,
+                        const uint32_t *d_gap_words, uint64_t n_segments,
+                        const hd_table *table, uint8_t *d_out,
+                        uint64_t n_symbols, void *d_workspace,
+                        size_t workspace_bytes, void *stream);
+
+/* Self-synchronisation scheme.  Replaces cuhd::CUHDGPUDecoder::decode
+ * (gpuhd/src/cuhd_gpu_decoder.cu:422-523; declared
+ * gpuhd/include/cuhd_gpu_decoder.h:24-32) = phases 1-4.  n_units may include
+ * the reference's trailing zero pad unit (gpuhd/src/cuhd_input_buffer.cc:
+ * 17-31).  The stream must start at bit 0 of unit 0 unless first_bit is set
+ * through hd_decode_selfsync_ex.  Synchronises the stream once (reads one
+ * 4-byte convergence flag), like the reference's phase-2 loop (:461-495). */
+hd_status hd_decode_selfsync(const uint32_t *d_units, uint64_t n_units,
+                             const hd_table *table, uint8_t *d_out,
+                             uint64_t n_symbols, void *d_workspace,
+                             size_t workspace_bytes, void *stream);
+
+/* Extended self-sync entry used by the multi-GPU sharding layer
+ * (replaces the slicing of gpuhd/multigpu_demo.cc:178-227): decode starts at
+ * bit `first_bit` (0..15) of unit 0; optionally returns the bit offset (0..15)
+ * at which the parse leaves the last COMPLETE 128-bit subsequence boundary
+ * `exit_subseq` (in subsequences from unit 0), and the number of symbols
+ * produced, in the two-word device array d_exit_info {exit_bit, reserved}
+ * and *d_count (uint64).  Pointers may be NULL. */
+hd_status hd_decode_selfsync_ex(const uint32_t *d_units, uint64_t n_units,
+                                uint32_t first_bit, const hd_table *table,
+                                uint8_t *d_out, uint64_t n_symbols,
+                                void *d_workspace, size_t workspace_bytes,
+                                uint64_t *d_count, void *stream);
+
+/* Synchronisation only (phases 1-2 of the reference, cuhd_gpu_decoder.cu:
+ * 145-327): writes the gap array of the stream -- for every 128-bit
+ * subsequence k>0 the bit offset of the first codeword starting in it, packed
+ * like the .huff gap array -- into d_gap_words_out (ceil(n_seg/8) words,
+ * n_seg = ceil(n_units/4)).  After this, hd_decode_gap decodes the stream. */
+hd_status hd_selfsync_gap_array(const uint32_t *d_units, uint64_t n_units,
+                                uint32_t first_bit, const hd_table *table,
+                                uint32_t *d_gap_words_out, void *d_workspace,
+                                size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------ .huff format
+ * Replaces the parser of Huffman_coding_Gap_arrays/decoder/src/huff.cpp:36-100
+ * and the writer of encoder/src/huff.cpp:186-202.  Pointers in the view alias
+ * the caller's buffer (payload may be 2-byte aligned only: copy before use as
+ * uint32). */
+typedef struct {
+    uint64_t symbol_count;
+    const hd_sym_len *symbols;   /* symbol_count pairs, file order */
+    uint32_t original_size;      /* decoded bytes */
+    uint32_t n_units;            /* compressed 32-bit units */
+    uint32_t n_segments;         /* 128-bit segments = gap elements */
+    const uint8_t *gap_words;    /* 4*ceil(n_segments/8) bytes, little endian */
+    const uint8_t *units;        /* 4*n_units bytes */
+    size_t total_bytes;          /* bytes of the image consumed */
+} hd_huff_view;
+
+hd_status hd_huff_parse(const void *file, size_t size, hd_huff_view *view);
+size_t hd_huff_image_bytes(uint64_t symbol_count, uint32_t n_units,
+                           uint32_t n_segments);
+
+/* Whole-file convenience with HOST buffers (the `./bin/decoder in out` shape,
+ * decoder/src/huff.cpp:31-129): parse, upload, decode on `device`, download.
+ * out_cap must be >= original_size.  *out_size receives original_size.
+ * timing_ms (may be NULL) receives {h2d, decode, d2h} like the reference's
+ * "HtoD,dec,DtoH" line (decoder.cu:803). */
+hd_status hd_huff_decode_host(const void *file, size_t size, uint8_t *out,
+                              size_t out_cap, size_t *out_size, int device,
+                              float timing_ms[3]);
+
+/* ---------------------------------------------------- encoders (input side)
+ * Host-side producers of both containers so that the CLIs and benchmarks can
+ * make inputs without the reference tree.  NOT the hot path.
+ * Length-limited (package-merge) code lengths + canonical codes:
+ * gpuhd/encoder/src/llhuffman_encoder.cc:17-198 (limit 11),
+ * Huffman_coding_Gap_arrays/encoder/src/package_merge.cpp:107-182 (limit 16).
+ * pairs_out receives up to 256 pairs in non-decreasing length order. */
+hd_status hd_build_code(const uint8_t *data, uint64_t n, uint32_t max_len,
+                        hd_sym_len *pairs_out, uint32_t *n_pairs_out);
+/* flat LUT of the code defined by pairs (canonical, list order) */
+hd_status hd_flat_lut_from_lengths(const hd_sym_len *pairs, uint32_t n_pairs,
+                                   uint32_t lut_bits, hd_lut_entry *lut_out);
+/* number of units / segments the packed stream needs */
+hd_status hd_encoded_size(const uint8_t *data, uint64_t n,
+                          const hd_sym_len *pairs, uint32_t n_pairs,
+                          uint64_t *bits_out);
+/* multi-threaded MSB-first packer (always flushes the tail, unlike reference
+ * defect D1); units_out: ceil(bits/32) units (+1 zero pad unit if
+ * pad_unit != 0); gap_words_out (may be NULL): ceil(ceil(bits/128)/8) words */
+hd_status hd_encode(const uint8_t *data, uint64_t n, const hd_sym_len *pairs,
+                    uint32_t n_pairs, uint32_t *units_out, uint64_t cap_units,
+                    int pad_unit, uint32_t *gap_words_out, int n_threads);
+/* write a .huff image; returns bytes written through *written */
+hd_status hd_huff_write(void *dst, size_t cap, const hd_sym_len *pairs,
+                        uint32_t n_pairs, uint32_t original_size,
+                        const uint32_t *units, uint32_t n_units,
+                        const uint32_t *gap_words, uint32_t n_segments,
+                        size_t *written);
+/* synthetic data with the distribution of generate.cpp:33-47 (byte =
+ * 'A'+U{0..3} with probability r, else U{0..255}); engine = mt19937_64 seeded
+ * per 1 MiB block from (seed, block) so generation is parallel and
+ * reproducible. */
+hd_status hd_generate(uint8_t *out, uint64_t n, double redundancy,
+                      uint64_t seed, int n_threads);
+
+/* --------------------------------------------------------------- multi GPU
+ * Sharding helpers (replace the naive split of gpuhd/multigpu_demo.cc:186-199).
+ * Pure host arithmetic: shard `rank` of `world` over n_segments 128-bit
+ * segments, aligned to whole tiles.  [seg_begin, seg_end). */
+void hd_shard_segments(uint64_t n_segments, uint32_t rank, uint32_t world,
+                       uint64_t *seg_begin, uint64_t *seg_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HD_B200_H_ */

@@ -1,0 +1,217 @@
+// hd_emul.cpp -- TEST INFRASTRUCTURE.  Single-steps, on the CPU, the very same
+// per-thread source the CUDA kernels run (csrc/hd_core.h) with the kernels'
+// block/tile structure re-enacted sequentially, so that control-flow and table
+// bugs are caught in this GPU-less container.  Never linked into the product
+// library; the product has no CPU path.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "hd_core.h"
+#include "hd_internal.h"
+
+using namespace hd;
+
+namespace {
+
+struct HostTables {
+    TableBlob blob;
+    DecodeTables T;
+    SyncLut L;
+};
+
+void bind(HostTables &h) {
+    const uint8_t *b = h.blob.bytes.data();
+    h.T.lut = reinterpret_cast<const uint32_t *>(b);
+    h.T.idx_shift = 32 - h.blob.lut_bits;
+    h.T.lut_bits = h.blob.lut_bits;
+    h.T.len_tab = b + h.blob.off_len;
+    h.T.order = b + h.blob.off_order;
+    h.T.lt = reinterpret_cast<const LongTables *>(b + h.blob.off_long);
+    h.L.lut = reinterpret_cast<const uint16_t *>(b + h.blob.off_sync);
+    h.L.idx_shift = 32 - h.blob.lut_bits;
+    h.L.lm = h.blob.lut_bits;
+    h.L.lt = h.T.lt;
+    h.L.order = h.T.order;
+    h.L.has_long = h.blob.has_long != 0;
+}
+
+bool make_tables(const hd_lut_entry *flat, uint32_t flat_bits, const hd_sym_len *pairs, uint32_t n_pairs,
+                 HostTables &h) {
+    HostCode c;
+    bool ok = flat ? code_from_flat_lut(flat, flat_bits, c) : code_from_pairs(pairs, n_pairs, c);
+    if (!ok) return false;
+    build_table_blob(c, h.blob);
+    bind(h);
+    return true;
+}
+
+struct HostSegLoader {
+    const uint32_t *units;
+    uint64_t n_units;
+    Seg4 operator()(uint64_t s) const {
+        Seg4 r{0, 0, 0, 0};
+        const uint64_t u = s * 4;
+        if (u < n_units) r.x = units[u];
+        if (u + 1 < n_units) r.y = units[u + 1];
+        if (u + 2 < n_units) r.z = units[u + 2];
+        if (u + 3 < n_units) r.w = units[u + 3];
+        return r;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+// Re-enactment of hd_decode_write_kernel: tiles of kTileThreads segments, per
+// thread decode_segment -> staging, exclusive scan, clamp, compact_to_tile into
+// a tile placed at the same 16-byte phase as the kernel, copy out.
+int64_t emul_decode_gap(const uint32_t *units, uint64_t n_units, const uint32_t *gap_words, uint64_t n_segments,
+                        uint32_t first_bit, const hd_lut_entry *flat, uint32_t flat_bits, const hd_sym_len *pairs,
+                        uint32_t n_pairs, uint8_t *out, uint64_t n_symbols, uint64_t out_addr_phase) {
+    HostTables h;
+    if (!make_tables(flat, flat_bits, pairs, n_pairs, h)) return -1;
+    const uint32_t min_len = h.blob.min_len ? h.blob.min_len : 1;
+    const uint32_t max_sym = (kSegmentBits + min_len - 1) / min_len;
+    const uint32_t stage_words = (max_sym + 1) / 4 + 2;
+    const uint32_t tile_bytes = ((kTileThreads * max_sym + 32) + 15) & ~15u;
+    std::vector<uint32_t> stage((size_t)stage_words * kTileThreads);
+    std::vector<uint8_t> tile(tile_bytes);
+    const uint64_t n_tiles = (n_segments + kTileThreads - 1) / kTileThreads;
+    uint64_t base = 0;
+    for (uint64_t tl = 0; tl < n_tiles; ++tl) {
+        // poison so that reads of never-written staging/tile bytes show up
+        std::fill(stage.begin(), stage.end(), 0xDEADBEEFu);
+        std::fill(tile.begin(), tile.end(), (uint8_t)0xEE);
+        uint32_t cnt[kTileThreads];
+        for (uint32_t t = 0; t < kTileThreads; ++t) {
+            const uint64_t g = tl * kTileThreads + t;
+            cnt[t] = 0;
+            if (g >= n_segments) continue;
+            HostSegLoader ld{units, n_units};
+            Seg4 w = ld(g);
+            Seg4 nx = ld(g + 1);
+            uint32_t start = first_bit;
+            if (g > 0) {
+                const uint64_t j = g - 1;
+                start = (gap_words[j >> 3] >> (4u * (uint32_t)(j & 7))) & 15u;
+            }
+            uint32_t c = h.blob.has_long
+                             ? decode_segment<true>(w.x, w.y, w.z, w.w, nx.x, start, h.T, stage.data() + t, kTileThreads)
+                             : decode_segment<false>(w.x, w.y, w.z, w.w, nx.x, start, h.T, stage.data() + t, kTileThreads);
+            if (c > max_sym) return -2;   // staging/tile sizing assumption violated
+            cnt[t] = c;
+        }
+        uint32_t excl = 0;
+        const uint32_t A = (uint32_t)((out_addr_phase + base) & 15u);
+        uint64_t tile_total = 0;
+        for (uint32_t t = 0; t < kTileThreads; ++t) {
+            uint64_t my_off = base + excl;
+            uint32_t c = cnt[t];
+            if (my_off >= n_symbols) c = 0;
+            else if (my_off + c > n_symbols) c = (uint32_t)(n_symbols - my_off);
+            if (c) {
+                if (A + excl + c > tile_bytes) return -3;
+                compact_to_tile(stage.data() + t, kTileThreads, c, tile.data(), A + excl);
+            }
+            excl += cnt[t];
+            tile_total += cnt[t];
+        }
+        uint64_t lim = base >= n_symbols ? 0 : n_symbols - base;
+        uint64_t tot = tile_total < lim ? tile_total : lim;
+        std::memcpy(out + base, tile.data() + A, tot);
+        base += tile_total;
+    }
+    return (int64_t)(base < n_symbols ? base : n_symbols);
+}
+
+// Re-enactment of hd_sync_chunks_kernel + hd_sync_seams_kernel rounds.
+// Returns the number of seam rounds run (>= 0) or negative on error.
+// rounds_out[0] = K1a intra-block iterations (max over blocks).
+int64_t emul_sync(const uint32_t *units, uint64_t n_units, uint32_t first_bit, const hd_lut_entry *flat,
+                  uint32_t flat_bits, const hd_sym_len *pairs, uint32_t n_pairs, uint32_t *gap_words_out,
+                  uint32_t *rounds_out) {
+    HostTables h;
+    if (!make_tables(flat, flat_bits, pairs, n_pairs, h)) return -1;
+    const uint64_t n_seg = (n_units + 3) / 4;
+    const uint64_t n_chunks = (n_seg + kChunkSegs - 1) / kChunkSegs;
+    const uint64_t n_blocks = (n_chunks + kSyncThreads - 1) / kSyncThreads;
+    HostSegLoader ld{units, n_units};
+    std::vector<uint8_t> blk_entry(n_blocks, 0);
+    uint32_t max_iters = 0;
+    // ---- K1a ----
+    for (uint64_t b = 0; b < n_blocks; ++b) {
+        uint32_t word[kSyncThreads] = {}, entry[kSyncThreads] = {}, s_exit[kSyncThreads] = {};
+        bool active[kSyncThreads];
+        bool merged;
+        for (uint32_t tid = 0; tid < kSyncThreads; ++tid) {
+            const uint64_t chunk = b * kSyncThreads + tid;
+            active[tid] = chunk < n_chunks;
+            entry[tid] = chunk == 0 ? first_bit : 0u;
+            if (active[tid]) word[tid] = sync_parse_chunk(ld, chunk, entry[tid], h.L, false, 0u, merged);
+            s_exit[tid] = word[tid] >> 28;
+        }
+        uint32_t iters = 0;
+        for (;;) {
+            ++iters;
+            uint32_t xin[kSyncThreads];
+            bool any = false;
+            for (uint32_t tid = 0; tid < kSyncThreads; ++tid)
+                xin[tid] = (tid == 0 || !active[tid]) ? entry[tid] : s_exit[tid - 1];
+            for (uint32_t tid = 0; tid < kSyncThreads; ++tid) {
+                if (xin[tid] == entry[tid]) continue;
+                any = true;
+                const uint64_t chunk = b * kSyncThreads + tid;
+                word[tid] = sync_parse_chunk(ld, chunk, xin[tid], h.L, true, word[tid], merged);
+                entry[tid] = xin[tid];
+                s_exit[tid] = word[tid] >> 28;
+            }
+            if (!any) break;
+        }
+        if (iters > max_iters) max_iters = iters;
+        for (uint32_t tid = 0; tid < kSyncThreads; ++tid)
+            if (active[tid]) gap_words_out[b * kSyncThreads + tid] = word[tid];
+        blk_entry[b] = (uint8_t)entry[0];
+    }
+    if (rounds_out) rounds_out[0] = max_iters;
+    // ---- K1b rounds until no block exit changes ----
+    int64_t rounds = 0;
+    for (;; ++rounds) {
+        uint32_t changed = 0;
+        for (uint64_t b = 1; b < n_blocks; ++b) {
+            const uint64_t c0 = b * kSyncThreads;
+            const uint32_t xin = gap_words_out[c0 - 1] >> 28;
+            if (xin == blk_entry[b]) continue;
+            uint64_t c_end = c0 + kSyncThreads;
+            if (c_end > n_chunks) c_end = n_chunks;
+            uint32_t entry = xin;
+            bool merged = false;
+            for (uint64_t c = c0; c < c_end; ++c) {
+                uint32_t w = sync_parse_chunk(ld, c, entry, h.L, true, gap_words_out[c], merged);
+                gap_words_out[c] = w;
+                if (merged) break;
+                entry = w >> 28;
+            }
+            blk_entry[b] = (uint8_t)xin;
+            if (!merged) ++changed;
+        }
+        if (!changed) break;
+        if ((uint64_t)rounds > n_blocks + 2) return -2;
+    }
+    return rounds + 1;
+}
+
+// table introspection for tests
+int emul_table_info(const hd_lut_entry *flat, uint32_t flat_bits, const hd_sym_len *pairs, uint32_t n_pairs,
+                    uint32_t info[4]) {
+    HostTables h;
+    if (!make_tables(flat, flat_bits, pairs, n_pairs, h)) return -1;
+    info[0] = h.blob.lut_bits;
+    info[1] = h.blob.min_len;
+    info[2] = h.blob.max_len;
+    info[3] = h.blob.has_long;
+    return 0;
+}
+
+}  // extern "C"
