@@ -388,4 +388,57 @@ hd_status hd_decode_selfsync(const uint32_t *d_units, uint64_t n_units, const hd
                                  nullptr, stream);
 }
 
+// Whole-file convenience with host buffers: the `./bin/decoder in out` shape of
+// Huffman_coding_Gap_arrays/decoder/src/huff.cpp:31-129 + decoder.cu:732-815
+// (allocate, H2D, one decode launch instead of 200, D2H).
+hd_status hd_huff_decode_host(const void *file, size_t size, uint8_t *out, size_t out_cap, size_t *out_size,
+                              int device, float timing_ms[3]) {
+    hd_huff_view v;
+    hd_status st = hd_huff_parse(file, size, &v);
+    if (st != HD_OK) return st;
+    if (out_size) *out_size = v.original_size;
+    if (!out || out_cap < v.original_size) return HD_ERR_INVALID;
+    if (device >= 0) HD_CUDA(cudaSetDevice(device));
+    if (v.original_size == 0 || v.n_units == 0) return HD_OK;
+    hd_table *tab = nullptr;
+    st = hd_table_from_lengths(v.symbols, (uint32_t)v.symbol_count, nullptr, &tab);
+    if (st != HD_OK) return st;
+    const size_t gap_bytes = align_up(((size_t)v.n_segments + 7) / 8 * 4, 256);
+    const size_t unit_bytes = align_up((size_t)v.n_units * 4, 256);
+    const size_t ws = ws_bytes(v.n_units, false);
+    uint8_t *d_in = nullptr, *d_out = nullptr, *d_ws = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    auto cleanup = [&]() {
+        if (d_in) cudaFree(d_in);
+        if (d_out) cudaFree(d_out);
+        if (d_ws) cudaFree(d_ws);
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+        hd_table_free(tab);
+    };
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_in), gap_bytes + unit_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&d_out), align_up(v.original_size, 256));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&d_ws), ws);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ev[i]);
+    if (e != cudaSuccess) { g_last_cuda = e; (void)cudaGetLastError(); cleanup(); return HD_ERR_CUDA; }
+    cudaEventRecord(ev[0], nullptr);
+    // gap words and units are uploaded to separately aligned regions (the file
+    // payload is only 2-byte aligned when the symbol count is odd)
+    e = cudaMemcpyAsync(d_in, v.gap_words, ((size_t)v.n_segments + 7) / 8 * 4, cudaMemcpyHostToDevice, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in + gap_bytes, v.units, (size_t)v.n_units * 4, cudaMemcpyHostToDevice, nullptr);
+    cudaEventRecord(ev[1], nullptr);
+    if (e == cudaSuccess) {
+        st = hd_decode_gap(reinterpret_cast<uint32_t *>(d_in + gap_bytes), v.n_units, reinterpret_cast<uint32_t *>(d_in),
+                           v.n_segments, tab, d_out, v.original_size, d_ws, ws, nullptr);
+        if (st != HD_OK) { cleanup(); return st; }
+    }
+    cudaEventRecord(ev[2], nullptr);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, v.original_size, cudaMemcpyDeviceToHost, nullptr);
+    cudaEventRecord(ev[3], nullptr);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess) { g_last_cuda = e; (void)cudaGetLastError(); cleanup(); return HD_ERR_CUDA; }
+    if (timing_ms) for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&timing_ms[i], ev[i], ev[i + 1]);
+    cleanup();
+    return HD_OK;
+}
+
 }  // extern "C"

@@ -111,13 +111,17 @@ hd_status hd_decode_selfsync(const uint32_t *d_units, uint64_t n_units,
                              uint64_t n_symbols, void *d_workspace,
                              size_t workspace_bytes, void *stream);
 
-/* Extended self-sync entry used by the multi-GPU sharding layer
- * (replaces the slicing of gpuhd/multigpu_demo.cc:178-227): decode starts at
- * bit `first_bit` (0..15) of unit 0; optionally returns the bit offset (0..15)
- * at which the parse leaves the last COMPLETE 128-bit subsequence boundary
- * `exit_subseq` (in subsequences from unit 0), and the number of symbols
- * produced, in the two-word device array d_exit_info {exit_bit, reserved}
- * and *d_count (uint64).  Pointers may be NULL. */
+/* Extended entries used by the multi-GPU sharding layer (they replace the
+ * slicing of gpuhd/multigpu_demo.cc:178-227): the shard's first segment starts
+ * at bit `first_bit` (0..15) instead of 0, and *d_count (device uint64, may be
+ * NULL) receives the number of symbols written -- the one value per GPU that
+ * the NCCL all-gather exchanges to place the shards' outputs. */
+hd_status hd_decode_gap_ex(const uint32_t *d_units, uint64_t n_units,
+                           const uint32_t *d_gap_words, uint64_t n_segments,
+                           uint32_t first_bit, const hd_table *table,
+                           uint8_t *d_out, uint64_t n_symbols,
+                           void *d_workspace, size_t workspace_bytes,
+                           uint64_t *d_count, void *stream);
 hd_status hd_decode_selfsync_ex(const uint32_t *d_units, uint64_t n_units,
                                 uint32_t first_bit, const hd_table *table,
                                 uint8_t *d_out, uint64_t n_symbols,
