@@ -46,8 +46,11 @@ ABI_SYMBOLS = [
     "hd_workspace_bytes_selfsync", "hd_decode_gap", "hd_decode_selfsync", "hd_decode_gap_ex",
     "hd_decode_selfsync_ex", "hd_selfsync_gap_array", "hd_huff_parse", "hd_huff_image_bytes",
     "hd_huff_decode_host", "hd_build_code", "hd_flat_lut_from_lengths", "hd_encoded_size", "hd_encode",
-    "hd_huff_write", "hd_generate", "hd_shard_segments",
+    "hd_huff_write", "hd_generate", "hd_shard_segments", "hd_host_decoder_create", "hd_host_decoder_destroy",
+    "hd_host_decode_selfsync", "hd_host_decode_huff", "hd_selfsync_decode_host", "hd_profile_enable",
+    "hd_profile_read", "hd_launch_count", "hd_decode_selfsync_shard",
 ]
+PROFILE_SLOTS = ("sync_chunks", "sync_seams", "decode_write", "reserved")
 
 
 def lib():
@@ -93,6 +96,17 @@ def lib():
     L.hd_generate.argtypes = [vp, u64, C.c_double, u64, C.c_int]
     L.hd_shard_segments.argtypes = [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]
     L.hd_shard_segments.restype = None
+    L.hd_host_decoder_create.argtypes = [C.c_int, u64, u64, C.POINTER(vp)]
+    L.hd_host_decoder_destroy.argtypes = [vp]
+    L.hd_host_decoder_destroy.restype = None
+    L.hd_host_decode_selfsync.argtypes = [vp, vp, u64, vp, u32, vp, u64, vp]
+    L.hd_host_decode_huff.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), vp]
+    L.hd_selfsync_decode_host.argtypes = [vp, u64, vp, u32, vp, u64, C.c_int, vp]
+    L.hd_profile_enable.argtypes = [C.c_int]
+    L.hd_profile_enable.restype = None
+    L.hd_profile_read.argtypes = [vp]
+    L.hd_launch_count.restype = u64
+    L.hd_decode_selfsync_shard.argtypes = [vp, u64, u64, u64, u32, vp, vp, u64, vp, sz, vp, vp]
     _lib = L
     return L
 
@@ -329,3 +343,67 @@ def decode_huff(image, device=-1):
     _check(lib().hd_huff_decode_host(img.ctypes.data, len(img), out.ctypes.data, len(out), C.byref(osz), device, t),
            "hd_huff_decode_host")
     return out[:osz.value], [t[0], t[1], t[2]]
+
+
+class HostDecoder:
+    """Host-buffer decoder (H2D + decode + D2H per call) with persistent device buffers: the region the reference
+    demos time (gpuhd/src/demo.cc:170-197; decoder.cu:760-803).  Inputs/outputs are numpy arrays or pinned torch
+    CPU tensors; everything goes through hd_host_decode_* of the C ABI."""
+
+    def __init__(self, max_units, max_symbols, device=0):
+        _torch()
+        h = C.c_void_p(None)
+        _check(lib().hd_host_decoder_create(device, int(max_units), int(max_symbols), C.byref(h)),
+               "hd_host_decoder_create")
+        self.handle = h
+
+    @staticmethod
+    def _ptr(a):
+        return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+
+    def decode_selfsync(self, units, flat_lut, out, n_symbols):
+        f = np.ascontiguousarray(flat_lut, dtype=np.uint8)
+        bits = int(f.shape[0]).bit_length() - 1
+        t = (C.c_float * 3)()
+        n_units = units.numel() if hasattr(units, "numel") else len(units)
+        _check(lib().hd_host_decode_selfsync(self.handle, self._ptr(units), n_units, f.ctypes.data, bits,
+                                             self._ptr(out), int(n_symbols), t), "hd_host_decode_selfsync")
+        return [t[0], t[1], t[2]]
+
+    def decode_huff(self, image, out):
+        t = (C.c_float * 3)()
+        osz = C.c_size_t(0)
+        n = image.numel() if hasattr(image, "numel") else len(image)
+        cap = out.numel() if hasattr(out, "numel") else len(out)
+        _check(lib().hd_host_decode_huff(self.handle, self._ptr(image), n, self._ptr(out), cap, C.byref(osz), t),
+               "hd_host_decode_huff")
+        return osz.value, [t[0], t[1], t[2]]
+
+    def close(self):
+        if self.handle:
+            lib().hd_host_decoder_destroy(self.handle)
+            self.handle = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def profile_enable(on=True):
+    lib().hd_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{slot: ms} of the kernels of the last profiled decode (hd_profile_read)."""
+    t = (C.c_float * 4)()
+    _check(lib().hd_profile_read(t), "hd_profile_read")
+    return dict(zip(PROFILE_SLOTS, [t[0], t[1], t[2], t[3]]))
+
+
+def launch_count():
+    return int(lib().hd_launch_count())
+
+
+from .sharding import ShardedSelfSyncDecoder, plan_shards, place_outputs, seams_ok, resolve_seams  # noqa: E402

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -16,6 +17,7 @@ using namespace hd;
 namespace {
 
 thread_local cudaError_t g_last_cuda = cudaSuccess;
+std::atomic<uint64_t> g_launches{0};   // kernels launched by this library (hd_launch_count)
 
 #define HD_CUDA(call)                              \
     do {                                           \
@@ -26,6 +28,32 @@ thread_local cudaError_t g_last_cuda = cudaSuccess;
             return HD_ERR_CUDA;                    \
         }                                          \
     } while (0)
+
+// ---- optional per-kernel device timing (hd_profile_*) -----------------------
+// bench.py turns this on for a separate pass to obtain the dominant kernel's
+// average launch duration on the launching stream; off by default (no events).
+struct Profiler {
+    bool on = false;
+    cudaEvent_t ev[HD_PROFILE_SLOTS][2] = {};
+    bool used[HD_PROFILE_SLOTS] = {};
+    bool created = false;
+};
+thread_local Profiler g_prof;
+
+struct ProfScope {
+    int slot;
+    cudaStream_t s;
+    bool active;
+    ProfScope(int slot_, cudaStream_t s_) : slot(slot_), s(s_), active(g_prof.on && !g_prof.used[slot_]) {
+        if (active) cudaEventRecord(g_prof.ev[slot][0], s);
+    }
+    ~ProfScope() {
+        if (active) {
+            cudaEventRecord(g_prof.ev[slot][1], s);
+            g_prof.used[slot] = true;
+        }
+    }
+};
 
 inline uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
@@ -134,16 +162,21 @@ hd_status launch_decode(const DecodeParams &p, size_t smem, cudaStream_t s) {
     uint64_t grid = (uint64_t)di.sm_count * per_sm;   // persistent: one wave, a multiple of the SM count
     if (grid > p.n_tiles) grid = p.n_tiles;
     kern<<<(unsigned)grid, kTileThreads, smem, s>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     HD_CUDA(cudaGetLastError());
     return HD_OK;
 }
 
 hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32_t *d_gap_words,
                          uint64_t n_segments, uint32_t first_bit, const hd_table *table, uint8_t *d_out,
-                         uint64_t n_symbols, const Workspace &w, uint64_t *d_count, cudaStream_t s) {
+                         uint64_t n_symbols, const Workspace &w, uint64_t *d_count, cudaStream_t s,
+                         uint64_t n_units_readable = 0, const uint32_t *entry_word = nullptr,
+                         uint64_t *shard_info = nullptr) {
     DecodeParams p;
     p.units = d_units;
-    p.n_units = n_units;
+    p.n_units = n_units_readable > n_units ? n_units_readable : n_units;
+    p.entry_word = entry_word;
+    p.shard_info = shard_info;
     p.gap_words = d_gap_words;
     p.n_segments = n_segments;
     p.first_bit = first_bit;
@@ -157,6 +190,7 @@ hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32
     const size_t smem = decode_smem_bytes(table, p.stage_words, p.tile_bytes);
     if ((int)smem > device_info().max_smem_optin) return HD_ERR_INVALID;
     HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes, s));
+    ProfScope prof(HD_PROFILE_DECODE_WRITE, s);
     return table->host.has_long ? launch_decode<true>(p, smem, s) : launch_decode<false>(p, smem, s);
 }
 
@@ -263,10 +297,11 @@ hd_status hd_decode_gap(const uint32_t *d_units, uint64_t n_units, const uint32_
 
 // phases 1+2: build the gap array of a stream by self-synchronisation
 static hd_status run_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit, const hd_table *table,
-                          uint32_t *d_gap_words, uint8_t *d_blk_entry, uint32_t *d_changed, cudaStream_t s) {
+                          uint32_t *d_gap_words, uint8_t *d_blk_entry, uint32_t *d_changed, cudaStream_t s,
+                          uint64_t n_units_readable = 0) {
     SyncParams p;
     p.units = d_units;
-    p.n_units = n_units;
+    p.n_units = n_units_readable > n_units ? n_units_readable : n_units;
     p.n_segments = div_up(n_units, kSegmentUnits);
     p.n_chunks = div_up(p.n_segments, kChunkSegs);
     p.n_blocks = div_up(p.n_chunks, kSyncThreads);
@@ -278,15 +313,21 @@ static hd_status run_sync(const uint32_t *d_units, uint64_t n_units, uint32_t fi
     const size_t smem = sync_smem_bytes(table);
     HD_CUDA(cudaFuncSetAttribute(hd_sync_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HD_CUDA(cudaFuncSetAttribute(hd_sync_seams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hd_sync_chunks_kernel<<<(unsigned)p.n_blocks, kSyncThreads, smem, s>>>(p);
+    {
+        ProfScope prof(HD_PROFILE_SYNC_CHUNKS, s);
+        hd_sync_chunks_kernel<<<(unsigned)p.n_blocks, kSyncThreads, smem, s>>>(p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     HD_CUDA(cudaGetLastError());
     if (p.n_blocks > 1) {
+        ProfScope prof(HD_PROFILE_SYNC_SEAMS, s);
         // two seam rounds up front: the first repairs the heads of the blocks,
         // the second only verifies (changed[1] == 0 <=> fixed point reached)
         const unsigned grid = (unsigned)div_up(p.n_blocks - 1, kSyncThreads);
         for (int round = 0; round < 2; ++round) {
             p.changed = d_changed + round;
             hd_sync_seams_kernel<<<grid, kSyncThreads, smem, s>>>(p);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
             HD_CUDA(cudaGetLastError());
         }
     }
@@ -298,7 +339,7 @@ static hd_status run_sync(const uint32_t *d_units, uint64_t n_units, uint32_t fi
 // synchronise inside a whole 128-chunk block.
 static hd_status finish_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit, const hd_table *table,
                              uint32_t *d_gap_words, uint8_t *d_blk_entry, uint32_t *d_changed, cudaStream_t s,
-                             bool *extra_rounds) {
+                             bool *extra_rounds, uint64_t n_units_readable = 0) {
     *extra_rounds = false;
     const uint64_t n_segments = div_up(n_units, kSegmentUnits);
     const uint64_t n_chunks = div_up(n_segments, kChunkSegs);
@@ -311,7 +352,7 @@ static hd_status finish_sync(const uint32_t *d_units, uint64_t n_units, uint32_t
     *extra_rounds = true;
     SyncParams p;
     p.units = d_units;
-    p.n_units = n_units;
+    p.n_units = n_units_readable > n_units ? n_units_readable : n_units;
     p.n_segments = n_segments;
     p.n_chunks = n_chunks;
     p.n_blocks = n_blocks;
@@ -325,6 +366,7 @@ static hd_status finish_sync(const uint32_t *d_units, uint64_t n_units, uint32_t
     for (uint64_t round = 0; round <= n_blocks; ++round) {
         HD_CUDA(cudaMemsetAsync(p.changed, 0, 4, s));
         hd_sync_seams_kernel<<<grid, kSyncThreads, smem, s>>>(p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
         HD_CUDA(cudaGetLastError());
         HD_CUDA(cudaMemcpyAsync(&h_changed, p.changed, 4, cudaMemcpyDeviceToHost, s));
         HD_CUDA(cudaStreamSynchronize(s));
@@ -382,10 +424,194 @@ hd_status hd_decode_selfsync_ex(const uint32_t *d_units, uint64_t n_units, uint3
     return st;
 }
 
+// One shard of a longer stream (multi-GPU): [halo | shard | right halo].  The
+// halo is parsed speculatively from bit 0 so that the parse is synchronised
+// when it enters the shard; the entry offset it reaches and the offset at which
+// the shard's parse leaves are reported so that neighbours can be checked
+// against each other (entry of rank g == exit of rank g-1).
+hd_status hd_decode_selfsync_shard(const uint32_t *d_units, uint64_t n_units_halo, uint64_t n_units_shard,
+                                   uint64_t n_units_readable, uint32_t first_bit, const hd_table *table,
+                                   uint8_t *d_out, uint64_t out_cap, void *d_workspace, size_t workspace_bytes,
+                                   uint64_t *d_shard_info, void *stream) {
+    const uint64_t n_units = n_units_halo + n_units_shard;
+    hd_status st = check_common(d_units, n_units, table, d_out, out_cap, d_workspace);
+    if (st != HD_OK) return st;
+    if (n_units_shard == 0 || first_bit > 15) return HD_ERR_INVALID;
+    if (n_units_halo % (kSegmentUnits * kChunkSegs)) return HD_ERR_INVALID;   // gap words must line up
+    if (n_units_readable < n_units) n_units_readable = n_units;
+    if (workspace_bytes < ws_bytes(n_units, true)) return HD_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Workspace w = carve(d_workspace, n_units, true);
+    HD_CUDA(cudaMemsetAsync(w.changed, 0, kCtrlBytes, s));
+    st = run_sync(d_units, n_units, n_units_halo ? 0u : first_bit, table, w.gap_words, w.blk_entry, w.changed, s,
+                  n_units_readable);
+    if (st != HD_OK) return st;
+    bool extra = false;
+    st = finish_sync(d_units, n_units, n_units_halo ? 0u : first_bit, table, w.gap_words, w.blk_entry, w.changed, s,
+                     &extra, n_units_readable);
+    if (st != HD_OK) return st;
+    const uint64_t halo_words = n_units_halo / (kSegmentUnits * kChunkSegs);
+    const uint32_t *gaps = w.gap_words + halo_words;
+    return run_gap_decode(d_units + n_units_halo, n_units_shard, gaps, div_up(n_units_shard, kSegmentUnits), first_bit,
+                          table, d_out, out_cap, w, nullptr, s, n_units_readable - n_units_halo,
+                          n_units_halo ? gaps - 1 : nullptr, d_shard_info);
+}
+
 hd_status hd_decode_selfsync(const uint32_t *d_units, uint64_t n_units, const hd_table *table, uint8_t *d_out,
                              uint64_t n_symbols, void *d_workspace, size_t workspace_bytes, void *stream) {
     return hd_decode_selfsync_ex(d_units, n_units, 0, table, d_out, n_symbols, d_workspace, workspace_bytes,
                                  nullptr, stream);
+}
+
+// ---------------------------------------------------------------- profiling
+uint64_t hd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void hd_profile_enable(int on) {
+    if (on && !g_prof.created) {
+        for (int i = 0; i < HD_PROFILE_SLOTS; ++i)
+            for (int j = 0; j < 2; ++j) cudaEventCreate(&g_prof.ev[i][j]);
+        g_prof.created = true;
+    }
+    g_prof.on = on != 0;
+    for (int i = 0; i < HD_PROFILE_SLOTS; ++i) g_prof.used[i] = false;
+}
+
+hd_status hd_profile_read(float ms_out[HD_PROFILE_SLOTS]) {
+    if (!ms_out || !g_prof.created) return HD_ERR_INVALID;
+    for (int i = 0; i < HD_PROFILE_SLOTS; ++i) {
+        ms_out[i] = 0.f;
+        if (!g_prof.used[i]) continue;
+        HD_CUDA(cudaEventSynchronize(g_prof.ev[i][1]));
+        HD_CUDA(cudaEventElapsedTime(&ms_out[i], g_prof.ev[i][0], g_prof.ev[i][1]));
+        g_prof.used[i] = false;
+    }
+    return HD_OK;
+}
+
+// ------------------------------------------------------- host-buffer decoder
+// Persistent device buffers + one stream: the per-call work is H2D, decode,
+// D2H -- the region gpuhd/src/demo.cc:170-197 ("Decompression time") and
+// decoder.cu:760-803 time, minus their per-call cudaMalloc.
+struct hd_host_decoder {
+    int device = 0;
+    uint64_t max_units = 0, max_symbols = 0;
+    uint8_t *d_units = nullptr, *d_gaps = nullptr, *d_out = nullptr, *d_ws = nullptr;
+    size_t ws_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+void hd_host_decoder_destroy(hd_host_decoder *h) {
+    if (!h) return;
+    if (h->d_units) cudaFree(h->d_units);
+    if (h->d_gaps) cudaFree(h->d_gaps);
+    if (h->d_out) cudaFree(h->d_out);
+    if (h->d_ws) cudaFree(h->d_ws);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+hd_status hd_host_decoder_create(int device, uint64_t max_units, uint64_t max_symbols, hd_host_decoder **out) {
+    if (!out || max_units == 0) return HD_ERR_INVALID;
+    if (device >= 0) HD_CUDA(cudaSetDevice(device));
+    hd_host_decoder *h = new (std::nothrow) hd_host_decoder();
+    if (!h) return HD_ERR_INVALID;
+    cudaGetDevice(&h->device);
+    h->max_units = max_units;
+    h->max_symbols = max_symbols;
+    h->ws_bytes = ws_bytes(max_units, true);
+    const uint64_t n_seg = div_up(max_units, kSegmentUnits);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&h->d_units), align_up(max_units * 4 + 16, 256));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h->d_gaps), align_up(div_up(n_seg, 8) * 4 + 16, 256));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h->d_out), align_up(max_symbols + 16, 256));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h->d_ws), h->ws_bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+    if (e != cudaSuccess) {
+        g_last_cuda = e;
+        (void)cudaGetLastError();
+        hd_host_decoder_destroy(h);
+        return HD_ERR_CUDA;
+    }
+    *out = h;
+    return HD_OK;
+}
+
+static hd_status host_decode_common(hd_host_decoder *h, const uint32_t *units, uint64_t n_units,
+                                    const uint8_t *gap_words, uint64_t n_segments, const hd_table *tab,
+                                    uint8_t *out, uint64_t n_symbols, float timing_ms[3]) {
+    if (n_units > h->max_units || n_symbols > h->max_symbols) return HD_ERR_INVALID;
+    HD_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    HD_CUDA(cudaEventRecord(h->ev[0], s));
+    HD_CUDA(cudaMemcpyAsync(h->d_units, units, n_units * 4, cudaMemcpyHostToDevice, s));
+    if (gap_words)
+        HD_CUDA(cudaMemcpyAsync(h->d_gaps, gap_words, div_up(n_segments, 8) * 4, cudaMemcpyHostToDevice, s));
+    HD_CUDA(cudaEventRecord(h->ev[1], s));
+    hd_status st;
+    if (gap_words)
+        st = hd_decode_gap(reinterpret_cast<uint32_t *>(h->d_units), n_units, reinterpret_cast<uint32_t *>(h->d_gaps),
+                           n_segments, tab, h->d_out, n_symbols, h->d_ws, h->ws_bytes, s);
+    else
+        st = hd_decode_selfsync(reinterpret_cast<uint32_t *>(h->d_units), n_units, tab, h->d_out, n_symbols, h->d_ws,
+                                h->ws_bytes, s);
+    if (st != HD_OK) return st;
+    HD_CUDA(cudaEventRecord(h->ev[2], s));
+    HD_CUDA(cudaMemcpyAsync(out, h->d_out, n_symbols, cudaMemcpyDeviceToHost, s));
+    HD_CUDA(cudaEventRecord(h->ev[3], s));
+    HD_CUDA(cudaStreamSynchronize(s));
+    if (timing_ms)
+        for (int i = 0; i < 3; ++i) HD_CUDA(cudaEventElapsedTime(&timing_ms[i], h->ev[i], h->ev[i + 1]));
+    return HD_OK;
+}
+
+hd_status hd_host_decode_selfsync(hd_host_decoder *h, const uint32_t *units, uint64_t n_units,
+                                  const hd_lut_entry *lut, uint32_t lut_bits, uint8_t *out, uint64_t n_symbols,
+                                  float timing_ms[3]) {
+    if (!h || !units || !lut || (!out && n_symbols)) return HD_ERR_INVALID;
+    if (n_units == 0) return n_symbols == 0 ? HD_OK : HD_ERR_INVALID;
+    HD_CUDA(cudaSetDevice(h->device));
+    hd_table *tab = nullptr;
+    hd_status st = hd_table_from_flat_lut(lut, lut_bits, h->stream, &tab);
+    if (st != HD_OK) return st;
+    st = host_decode_common(h, units, n_units, nullptr, 0, tab, out, n_symbols, timing_ms);
+    cudaStreamSynchronize(h->stream);
+    hd_table_free(tab);
+    return st;
+}
+
+hd_status hd_host_decode_huff(hd_host_decoder *h, const void *file, size_t size, uint8_t *out, size_t out_cap,
+                              size_t *out_size, float timing_ms[3]) {
+    if (!h) return HD_ERR_INVALID;
+    hd_huff_view v;
+    hd_status st = hd_huff_parse(file, size, &v);
+    if (st != HD_OK) return st;
+    if (out_size) *out_size = v.original_size;
+    if (!out || out_cap < v.original_size) return HD_ERR_INVALID;
+    if (v.original_size == 0 || v.n_units == 0) return HD_OK;
+    HD_CUDA(cudaSetDevice(h->device));
+    hd_table *tab = nullptr;
+    st = hd_table_from_lengths(v.symbols, (uint32_t)v.symbol_count, h->stream, &tab);
+    if (st != HD_OK) return st;
+    // the payload may be only 2-byte aligned in the file image; cudaMemcpy does not care
+    st = host_decode_common(h, reinterpret_cast<const uint32_t *>(v.units), v.n_units, v.gap_words, v.n_segments, tab,
+                            out, v.original_size, timing_ms);
+    cudaStreamSynchronize(h->stream);
+    hd_table_free(tab);
+    return st;
+}
+
+// One-shot `./bin/demo` shape (gpuhd/src/demo.cc:155-197): allocate, H2D, decode, D2H, free.
+hd_status hd_selfsync_decode_host(const uint32_t *units, uint64_t n_units, const hd_lut_entry *lut,
+                                  uint32_t lut_bits, uint8_t *out, uint64_t n_symbols, int device,
+                                  float timing_ms[3]) {
+    hd_host_decoder *h = nullptr;
+    hd_status st = hd_host_decoder_create(device, n_units ? n_units : 1, n_symbols, &h);
+    if (st != HD_OK) return st;
+    st = hd_host_decode_selfsync(h, units, n_units, lut, lut_bits, out, n_symbols, timing_ms);
+    hd_host_decoder_destroy(h);
+    return st;
 }
 
 // Whole-file convenience with host buffers: the `./bin/decoder in out` shape of

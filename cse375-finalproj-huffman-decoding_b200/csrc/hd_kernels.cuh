@@ -58,10 +58,12 @@ struct TableDev {
 
 struct DecodeParams {
     const uint32_t *units;
-    uint64_t n_units;
+    uint64_t n_units;            // units that may be READ (includes a right halo when the stream continues)
     const uint32_t *gap_words;   // element i = start offset of segment i+1
-    uint64_t n_segments;
-    uint32_t first_bit;          // start offset of segment 0
+    uint64_t n_segments;         // segments to DECODE
+    uint32_t first_bit;          // start offset of segment 0 ...
+    const uint32_t *entry_word;  // ... unless set: start offset of segment 0 = *entry_word >> 28
+    uint64_t *shard_info;        // optional {count, entry_bit, exit_bit} for the multi-GPU seam check
     TableDev table;
     uint8_t *out;
     uint64_t n_symbols;
@@ -75,7 +77,7 @@ struct DecodeParams {
 
 struct SyncParams {
     const uint32_t *units;
-    uint64_t n_units;
+    uint64_t n_units;            // units that may be READ
     uint64_t n_segments;
     uint64_t n_chunks;           // ceil(n_segments / kChunkSegs)
     uint64_t n_blocks;           // ceil(n_chunks / kSyncThreads)
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(kTileThreads) hd_decode_write_kernel(const Dec
                 if (u + 1 < p.n_units) r1 = __ldg(p.units + u + 1);
                 if (u + 2 < p.n_units) r2 = __ldg(p.units + u + 2);
             }
-            if (g == 0) start = p.first_bit;
+            if (g == 0) start = p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit;
             else {
                 const uint64_t j = g - 1;
                 start = (__ldg(p.gap_words + (j >> 3)) >> (4u * (uint32_t)(j & 7))) & 15u;
@@ -220,9 +222,16 @@ __global__ void __launch_bounds__(kTileThreads) hd_decode_write_kernel(const Dec
                 s_total = (uint32_t)agg;
                 // the previous tile's TMA store must have finished READING s_tile
                 if (store_pending) tma_bulk_wait_read0();
-                if (p.count_out && tile + 1 == p.n_tiles) {
+                if (tile + 1 == p.n_tiles) {
                     uint64_t tot = excl + agg;
-                    *p.count_out = tot < p.n_symbols ? tot : p.n_symbols;
+                    tot = tot < p.n_symbols ? tot : p.n_symbols;
+                    if (p.count_out) *p.count_out = tot;
+                    if (p.shard_info) {
+                        p.shard_info[0] = tot;
+                        p.shard_info[1] = p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit;
+                        const uint64_t j = p.n_segments - 1;   // offset at which the parse leaves the shard
+                        p.shard_info[2] = (__ldg(p.gap_words + (j >> 3)) >> (4u * (uint32_t)(j & 7))) & 15u;
+                    }
                 }
             }
         }

@@ -128,6 +128,24 @@ hd_status hd_decode_selfsync_ex(const uint32_t *d_units, uint64_t n_units,
                                 void *d_workspace, size_t workspace_bytes,
                                 uint64_t *d_count, void *stream);
 
+/* One shard of a longer stream, for multi-GPU decode (replaces the per-GPU
+ * slicing of gpuhd/multigpu_demo.cc:186-199, which cuts units and symbols
+ * independently and therefore fails).  d_units -> [left halo | shard | right
+ * halo]: n_units_halo (multiple of 32) units before the shard are parsed
+ * speculatively so that the parse is synchronised when it enters the shard;
+ * units up to n_units_readable (>= halo+shard; the last codeword of the shard
+ * may end in the next unit) may be read.  Rank 0 passes halo 0 and first_bit.
+ * d_shard_info receives {symbols written, entry bit offset used, bit offset at
+ * which the parse leaves the shard}: ranks all-gather these (NCCL), check
+ * entry[g] == exit[g-1] and exclusive-scan the counts for output placement. */
+hd_status hd_decode_selfsync_shard(const uint32_t *d_units, uint64_t n_units_halo,
+                                   uint64_t n_units_shard,
+                                   uint64_t n_units_readable, uint32_t first_bit,
+                                   const hd_table *table, uint8_t *d_out,
+                                   uint64_t out_cap, void *d_workspace,
+                                   size_t workspace_bytes,
+                                   uint64_t *d_shard_info, void *stream);
+
 /* Synchronisation only (phases 1-2 of the reference, cuhd_gpu_decoder.cu:
  * 145-327): writes the gap array of the stream -- for every 128-bit
  * subsequence k>0 the bit offset of the first codeword starting in it, packed
@@ -166,6 +184,47 @@ size_t hd_huff_image_bytes(uint64_t symbol_count, uint32_t n_units,
 hd_status hd_huff_decode_host(const void *file, size_t size, uint8_t *out,
                               size_t out_cap, size_t *out_size, int device,
                               float timing_ms[3]);
+
+/* Host-buffer decoder with persistent device buffers and its own stream: per
+ * call = H2D + decode + D2H, the region the reference demos time
+ * (gpuhd/src/demo.cc:170-197 "Decompression time"; decoder.cu:760-803
+ * "HtoD,dec,DtoH"), without their per-call cudaMalloc.  Host pointers should
+ * be pinned for full PCIe rate (the reference pins too, decoder/src/huff.cpp:
+ * 44,88).  timing_ms (may be NULL) = {h2d, decode, d2h} device milliseconds. */
+typedef struct hd_host_decoder hd_host_decoder;
+hd_status hd_host_decoder_create(int device, uint64_t max_units,
+                                 uint64_t max_symbols, hd_host_decoder **out);
+void hd_host_decoder_destroy(hd_host_decoder *h);
+/* == CUHDGPUInputBuffer::cpy_host_to_device + CUHDGPUDecoder::decode +
+ *    CUHDGPUOutputBuffer::cpy_device_to_host (gpuhd/src/demo.cc:183-195) */
+hd_status hd_host_decode_selfsync(hd_host_decoder *h, const uint32_t *units,
+                                  uint64_t n_units, const hd_lut_entry *lut,
+                                  uint32_t lut_bits, uint8_t *out,
+                                  uint64_t n_symbols, float timing_ms[3]);
+/* == decoder_l1_l2 on a parsed .huff image (decoder/src/huff.cpp:81-118) */
+hd_status hd_host_decode_huff(hd_host_decoder *h, const void *file,
+                              size_t size, uint8_t *out, size_t out_cap,
+                              size_t *out_size, float timing_ms[3]);
+/* one-shot `./bin/demo <gpu> <MB>` shape: allocate, H2D, decode, D2H, free */
+hd_status hd_selfsync_decode_host(const uint32_t *units, uint64_t n_units,
+                                  const hd_lut_entry *lut, uint32_t lut_bits,
+                                  uint8_t *out, uint64_t n_symbols, int device,
+                                  float timing_ms[3]);
+
+/* --------------------------------------------------------------- profiling
+ * Optional per-kernel device timing (the reference has cudaEvent TIMER_START/
+ * TIMER_STOP around its kernel, decoder/include/cu_timer.h:10-37).  When
+ * enabled on the calling thread, the next decode records one event pair per
+ * kernel class on the decode stream; hd_profile_read returns the elapsed
+ * milliseconds per slot and re-arms. */
+#define HD_PROFILE_SYNC_CHUNKS 0   /* K1a */
+#define HD_PROFILE_SYNC_SEAMS 1    /* K1b (both rounds) */
+#define HD_PROFILE_DECODE_WRITE 2  /* K4 */
+#define HD_PROFILE_SLOTS 4
+/* kernels launched by this library in this process so far */
+uint64_t hd_launch_count(void);
+void hd_profile_enable(int on);
+hd_status hd_profile_read(float ms_out[HD_PROFILE_SLOTS]);
 
 /* ---------------------------------------------------- encoders (input side)
  * Host-side producers of both containers so that the CLIs and benchmarks can

@@ -306,3 +306,98 @@ def test_1GiB_gap_roundtrip(hd, torch_cuda):
     n = 1 << 30
     same, cnt = _roundtrip_large(hd, torch_cuda, n, 0.5, "gap")
     assert same and cnt == n
+
+
+# ---------------------------------------------------------------- multi-GPU shard entry (ranks emulated on one device)
+def _sharded_selfsync(hd, units, lut, n, world, halo_segments):
+    tab = hd.Codetable(flat_lut=lut)
+    decs = [hd.ShardedSelfSyncDecoder(units, tab, n, g, world, dist=None, halo_segments=halo_segments)
+            for g in range(world)]
+    for d in decs:
+        d._decode()
+    infos = [d.info.cpu().numpy().copy() for d in decs]
+
+    def gather():
+        return np.stack([d.info.cpu().numpy() for d in decs])
+
+    redone = []
+    for g, d in enumerate(decs):   # every emulated rank runs the same protocol; only rank g's redecode acts
+        def redecode(first_bit, d=d, g=g):
+            d._decode(first_bit=first_bit, halo=False)
+            redone.append(g)
+        placed = hd.resolve_seams(g, world, gather(), gather, redecode, n)
+    parts = [d.out[:placed[g][1]].cpu().numpy() for g, d in enumerate(decs)]
+    tab.close()
+    return np.concatenate(parts), infos, placed, redone
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_selfsync_shards_with_halo(hd, torch_cuda, world):
+    n = 5_000_000
+    data = O.generate(n, 0.5, seed=41)
+    pairs = hd.build_code(data, 11)
+    lut = hd.flat_lut(pairs, 11)
+    units, bits = hd.encode(data, pairs, pad_unit=True)
+    whole, infos, placed, redone = _sharded_selfsync(hd, units, lut, n, world, 4096)
+    assert redone == []                                  # the halo synchronised every seam
+    assert hd.seams_ok(infos) == []
+    assert sum(c for _, c in placed) == n
+    assert np.array_equal(whole, data)
+    # entry offsets equal the oracle's true parse
+    off, cnt = O.sync_points(units, lut, n)
+    plan = hd.plan_shards(len(units), world)
+    for g in range(1, world):
+        assert int(infos[g][1]) == int(off[plan[g][0]])
+
+
+def test_selfsync_shards_repair_when_code_never_synchronises(hd, torch_cuda):
+    """All-3-bit code: the halo cannot synchronise, the seam check catches it and the shard is re-decoded from the
+    predecessor's exact exit offset (sequential chain across ranks)."""
+    pairs = cases.fixed_length_code(8, 3)
+    n = 2_000_003
+    data = cases.data_for_pairs(pairs, n, seed=6)
+    units, gw, bits, lut = cases.oracle_stream(data, pairs, pad_unit=True)
+    whole, infos, placed, redone = _sharded_selfsync(hd, units, lut, n, 4, 1024)
+    assert np.array_equal(whole, data)
+    assert sum(c for _, c in placed) == n
+
+
+def test_host_decoder_selfsync_and_huff(hd, torch_cuda):
+    torch = torch_cuda
+    n = 3_000_001
+    data = O.generate(n, 0.5, seed=51)
+    pairs = hd.build_code(data, 11)
+    lut = hd.flat_lut(pairs, 11)
+    units, bits = hd.encode(data, pairs, pad_unit=True)
+    hdec = hd.HostDecoder(len(units), n, device=0)
+    h_units = torch.from_numpy(units.view(np.int32)).pin_memory()
+    h_out = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        t = hdec.decode_selfsync(h_units, lut, h_out, n)
+        assert np.array_equal(h_out.numpy(), data) and all(x >= 0 for x in t)
+    pairs16 = hd.build_code(data, 16)
+    units16, gaps, _ = hd.encode(data, pairs16, want_gaps=True)
+    image = hd.huff_write(pairs16, n, units16, gaps)
+    out2 = np.zeros(n, dtype=np.uint8)
+    size, t = hdec.decode_huff(image, out2)
+    assert size == n and np.array_equal(out2, data)
+    hdec.close()
+
+
+def test_profile_hooks_report_kernel_times(hd, torch_cuda):
+    n = 2_000_000
+    data = O.generate(n, 0.5, seed=61)
+    pairs = hd.build_code(data, 11)
+    units, bits = hd.encode(data, pairs, pad_unit=True)
+    tab = hd.Codetable(flat_lut=hd.flat_lut(pairs, 11))
+    d_units = hd.to_device_units(units)
+    dec = hd.Decoder(d_units.numel(), selfsync=True)
+    before = hd.launch_count()
+    hd.profile_enable(True)
+    out = dec.decode_selfsync(d_units, tab, n)
+    ms = hd.profile_read()
+    hd.profile_enable(False)
+    assert hd.launch_count() - before >= 2
+    assert ms["decode_write"] > 0 and ms["sync_chunks"] > 0
+    assert np.array_equal(out.cpu().numpy(), data)
+    tab.close()
