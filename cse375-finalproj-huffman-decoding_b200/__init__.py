@@ -48,7 +48,7 @@ ABI_SYMBOLS = [
     "hd_huff_decode_host", "hd_build_code", "hd_flat_lut_from_lengths", "hd_encoded_size", "hd_encode",
     "hd_huff_write", "hd_generate", "hd_shard_segments", "hd_host_decoder_create", "hd_host_decoder_destroy",
     "hd_host_decode_selfsync", "hd_host_decode_huff", "hd_selfsync_decode_host", "hd_profile_enable",
-    "hd_profile_read", "hd_launch_count", "hd_decode_selfsync_shard",
+    "hd_profile_read", "hd_launch_count", "hd_decode_selfsync_shard", "hd_set_tuning",
 ]
 PROFILE_SLOTS = ("sync_chunks", "sync_seams", "decode_write", "reserved")
 
@@ -106,6 +106,8 @@ def lib():
     L.hd_profile_enable.restype = None
     L.hd_profile_read.argtypes = [vp]
     L.hd_launch_count.restype = u64
+    L.hd_set_tuning.argtypes = [C.c_int]
+    L.hd_set_tuning.restype = None
     L.hd_decode_selfsync_shard.argtypes = [vp, u64, u64, u64, u32, vp, vp, u64, vp, sz, vp, vp]
     _lib = L
     return L
@@ -296,12 +298,12 @@ class Decoder:
                                            self.count.data_ptr(), _stream_ptr(torch)), "hd_decode_selfsync")
         return out
 
-    def decode_gap(self, d_units, d_gap_words, table, n_symbols, out=None, first_bit=0):
+    def decode_gap(self, d_units, d_gap_words, table, n_symbols, out=None, first_bit=0, n_segments=None):
         """decoder_l1_l2 / gpu_dec_l1_l2 (Huffman_coding_Gap_arrays/decoder/src/decoder.cu:454-815)."""
         torch = _torch()
         if out is None:
             out = torch.empty(n_symbols, dtype=torch.uint8, device="cuda")
-        n_seg = (d_units.numel() + 3) // 4
+        n_seg = (d_units.numel() + 3) // 4 if n_segments is None else int(n_segments)
         _check(lib().hd_decode_gap_ex(d_units.data_ptr(), d_units.numel(),
                                       d_gap_words.data_ptr() if d_gap_words is not None else None, n_seg,
                                       first_bit, table.handle, out.data_ptr(), n_symbols, self.ws_ptr,
@@ -400,6 +402,10 @@ def profile_read():
     t = (C.c_float * 4)()
     _check(lib().hd_profile_read(t), "hd_profile_read")
     return dict(zip(PROFILE_SLOTS, [t[0], t[1], t[2], t[3]]))
+
+
+def set_tuning(segs_per_thread=0):
+    lib().hd_set_tuning(int(segs_per_thread))
 
 
 def launch_count():

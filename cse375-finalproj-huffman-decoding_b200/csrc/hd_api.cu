@@ -138,22 +138,50 @@ DeviceInfo device_info() {
     return d;
 }
 
-size_t decode_smem_bytes(const hd_table *t, uint32_t &stage_words, uint32_t &tile_bytes) {
+// K4 geometry for a table: segments per thread and the smem carve-up (must match the kernel)
+struct DecodeGeom {
+    int segs;
+    uint32_t stage_words, tile_bytes;
+    size_t smem;
+};
+
+DecodeGeom decode_geom(const hd_table *t, int segs) {
+    DecodeGeom g;
+    g.segs = segs;
     const uint32_t min_len = std::max<uint32_t>(1, t->host.min_len);
-    const uint32_t max_sym = (kSegmentBits + min_len - 1) / min_len;   // symbols starting inside one segment
-    stage_words = (max_sym + 1) / 4 + 2;
-    tile_bytes = (uint32_t)align_up((size_t)kTileThreads * max_sym + 32, 16);
-    return (4u << t->host.lut_bits) + 512 + align_up(sizeof(LongTables), 16) +
-           (size_t)stage_words * kTileThreads * 4 + tile_bytes;
+    // a chunk decodes bits [entry, 128*segs + next_entry), entry offsets <= 15, plus the uncounted 2nd symbol of the
+    // last lookup and the always-written second byte
+    const uint32_t max_sym = (kSegmentBits * segs + 15 + min_len - 1) / min_len + 2;
+    g.stage_words = (max_sym + 8) / 4 + 1;
+    const uint32_t tile_sym = (kTileThreads * kSegmentBits * segs + 15 + min_len - 1) / min_len + 2;
+    g.tile_bytes = (uint32_t)align_up((size_t)tile_sym + 32, 16);
+    g.smem = (4u << t->host.lut_bits) + (t->host.has_long ? 256 + align_up(sizeof(LongTables), 16) : 0) +
+             (size_t)(4 * segs + 3) * kTileThreads * 4 + 1024 /* staging alignment slack */ +
+             (size_t)g.stage_words * kTileThreads * 4 + g.tile_bytes;
+    return g;
+}
+
+int g_force_segs = 0;   // hd_set_tuning: 0 = automatic
+
+DecodeGeom pick_geom(const hd_table *t, int max_smem) {
+    if (g_force_segs == 1 || g_force_segs == 2 || g_force_segs == 4) {
+        DecodeGeom g = decode_geom(t, g_force_segs);
+        if ((int)g.smem <= max_smem) return g;
+    }
+    // two segments per thread halve the look-back/barrier rate and even out the per-thread symbol counts; fall back to
+    // one when the worst-case staging (1-bit codes) would leave fewer than two CTAs per SM
+    DecodeGeom g2 = decode_geom(t, 2);
+    if (g2.smem * 2 + 2048 <= (size_t)max_smem) return g2;
+    return decode_geom(t, 1);
 }
 
 size_t sync_smem_bytes(const hd_table *t) {
     return align_up(2u << t->host.lut_bits, 16) + 256 + align_up(sizeof(LongTables), 16);
 }
 
-template <bool LONG>
+template <int SEGS, bool LONG>
 hd_status launch_decode(const DecodeParams &p, size_t smem, cudaStream_t s) {
-    auto kern = hd_decode_write_kernel<LONG>;
+    auto kern = hd_decode_write_kernel<SEGS, LONG>;
     HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     HD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem));
@@ -185,13 +213,20 @@ hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32
     p.n_symbols = n_symbols;
     p.tile_status = w.tile_status;
     p.tile_counter = w.tile_counter;
-    p.n_tiles = div_up(n_segments, kTileThreads);
+    const DecodeGeom g = pick_geom(table, device_info().max_smem_optin);
+    if ((int)g.smem > device_info().max_smem_optin) return HD_ERR_INVALID;
+    p.n_tiles = div_up(div_up(n_segments, (uint64_t)g.segs), kTileThreads);
     p.count_out = d_count;
-    const size_t smem = decode_smem_bytes(table, p.stage_words, p.tile_bytes);
-    if ((int)smem > device_info().max_smem_optin) return HD_ERR_INVALID;
+    p.stage_words = g.stage_words;
+    p.tile_bytes = g.tile_bytes;
     HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes, s));
     ProfScope prof(HD_PROFILE_DECODE_WRITE, s);
-    return table->host.has_long ? launch_decode<true>(p, smem, s) : launch_decode<false>(p, smem, s);
+    const bool lng = table->host.has_long != 0;
+    switch (g.segs) {
+        case 1: return lng ? launch_decode<1, true>(p, g.smem, s) : launch_decode<1, false>(p, g.smem, s);
+        case 2: return lng ? launch_decode<2, true>(p, g.smem, s) : launch_decode<2, false>(p, g.smem, s);
+        default: return lng ? launch_decode<4, true>(p, g.smem, s) : launch_decode<4, false>(p, g.smem, s);
+    }
 }
 
 hd_status check_common(const uint32_t *d_units, uint64_t n_units, const hd_table *table, const uint8_t *d_out,
@@ -280,7 +315,9 @@ hd_status hd_decode_gap_ex(const uint32_t *d_units, uint64_t n_units, const uint
     hd_status st = check_common(d_units, n_units, table, d_out, n_symbols, d_workspace);
     if (st != HD_OK) return st;
     if (n_units == 0) return HD_OK;
-    if (n_segments != div_up(n_units, kSegmentUnits) || first_bit > 15) return HD_ERR_INVALID;
+    // n_units = units that may be READ; a shard of a longer stream passes fewer segments than that so that its
+    // last codeword can end in the right halo (the stop rule is "codeword STARTS inside the segment")
+    if (n_segments == 0 || n_segments > div_up(n_units, kSegmentUnits) || first_bit > 15) return HD_ERR_INVALID;
     if (n_segments > 1 && !d_gap_words) return HD_ERR_INVALID;
     if (workspace_bytes < ws_bytes(n_units, false)) return HD_ERR_WORKSPACE;
     Workspace w = carve(d_workspace, n_units, false);
@@ -462,6 +499,9 @@ hd_status hd_decode_selfsync(const uint32_t *d_units, uint64_t n_units, const hd
     return hd_decode_selfsync_ex(d_units, n_units, 0, table, d_out, n_symbols, d_workspace, workspace_bytes,
                                  nullptr, stream);
 }
+
+// ------------------------------------------------------------------ tuning
+void hd_set_tuning(int segs_per_thread) { g_force_segs = segs_per_thread; }
 
 // ---------------------------------------------------------------- profiling
 uint64_t hd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -49,48 +49,71 @@ struct DecodeTables {
     const uint8_t *order;
 };
 
-// Decode one 128-bit segment held in r0..r3 (+ r4 = first unit of the next
-// segment) starting at bit `start` (0..15).  Symbols are appended to the
-// thread's private staging words st[0], st[stride], st[2*stride], ...
-// (little-endian bytes).  Returns the number of symbols whose codeword STARTS
-// inside the segment (the stop rule of decoder.cu:672: start bit < 128).
+// ---- "shared memory" byte/word accessors --------------------------------------
+// On the device `a` is an absolute 32-bit shared-window address (so that address
+// arithmetic needs no base add and maps 1:1 onto STS/LDS operands); in the CPU
+// emulator it is an offset into a host arena that mimics the CTA's smem.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void smem_st_u8(uint32_t a, uint32_t v, uint8_t *) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v));
+}
+#else
+inline void smem_st_u8(uint32_t a, uint32_t v, uint8_t *arena) { arena[a] = (uint8_t)v; }
+#endif
+
+// Bits of a staging address that select the thread's column (thread t owns byte
+// lanes [4t, 4t+3] of every 1 KiB staging row: bank == lane, conflict free).
+constexpr uint32_t kColBits = (kTileThreads - 1u) << 2;
+
+// Decode one chunk (SEGS consecutive 128-bit segments of one thread) in a single
+// flattened loop.  The chunk's units sit in the thread's column of the
+// transposed input tile: word w at in_col[w * kTileThreads] (conflict-free
+// refills); words past the chunk (the next chunk's first two) must be present.
+// Decoding starts at bit `entry` (< 32) and runs until the position reaches
+// `stop` = chunk bits + entry offset of the NEXT chunk, i.e. exactly to the
+// codeword boundary at which the successor starts (with an exact gap array this
+// is the stop rule of decoder.cu:672 -- decode every codeword that STARTS inside
+// the chunk -- because the last such codeword ends at that boundary).
 //
-// State word S = bit position | symbol count << 8 so that one add of the LUT
-// entry's upper half advances both; bit 7 of S = "position >= 128", bit 5
-// flips when a 32-bit unit boundary is crossed (window refill), bit 10 flips
-// when the pending output word fills up.
+// Symbols are stored one byte at a time into the thread's staging column:
+// symbol i at row i/4, byte i%4 of the column.  The running store address A
+// keeps the column bits; OR-ing them to ones before an add lets the carry out of
+// the two byte bits ripple through the column field into the row field, so
+// "advance by n symbols" is one add plus two logic ops.  A two-symbol LUT entry
+// always stores both bytes; the second is simply overwritten by the next lookup
+// when the entry held one symbol.  Returns the number of symbols.
 template <bool LONG>
-HD_HD uint32_t decode_segment(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t start,
-                              const DecodeTables &T, uint32_t *st, uint32_t stride) {
-    uint32_t S = start;
-    uint32_t acc = 0;
-    uint32_t e;
-    do {
-        const uint32_t win = funnel_l(r1, r0, S);   // next 32 stream bits
+HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t stop, const DecodeTables &T,
+                            uint32_t stage_addr, uint8_t *arena) {
+    uint32_t w0 = in_col[0], w1 = in_col[kTileThreads], w2 = in_col[2 * kTileThreads];
+    const uint32_t *nxt = in_col + 3 * kTileThreads;
+    const uint32_t col = stage_addr & kColBits;
+    uint32_t A = stage_addr;
+    uint32_t pos = entry;
+    uint32_t e = 0;
+    while (pos < stop) {
+        const uint32_t win = funnel_l(w1, w0, pos);   // next 32 stream bits
         e = T.lut[win >> T.idx_shift];
         if (LONG) {
             if ((e >> 16) == 0) e = resolve_long(win, T.lut_bits, T.lt, T.order);
         }
-        const uint32_t Sn = S + (e >> 16);
-        const uint32_t sh = (S >> 5) & 24u;   // 8 * (count & 3)
-        const uint32_t sy = e & 0xffffu;
-        const uint32_t lo = acc | (sy << sh);
-        const uint32_t hi = funnel_l(sy, 0u, sh);   // sy >> (32 - sh), 0 when sh == 0
-        const uint32_t x = Sn ^ S;
-        const bool full = (x & 0x400u) != 0;
-        if (full) { *st = lo; st += stride; }
-        acc = full ? hi : lo;
-        if (x & 32u) { r0 = r1; r1 = r2; r2 = r3; r3 = r4; }
-        S = Sn;
-    } while (!(S & 0x80u));
-    // a second symbol of the last lookup that starts at/after bit 128 belongs to
-    // the next segment
-    if ((e >> 24) == 2) {
-        const uint32_t len1 = T.len_tab[(e >> 8) & 0xffu];
-        if ((S & 0xffu) - len1 >= kSegmentBits) S -= 0x100u;
+        const uint32_t u = A | kColBits;
+        smem_st_u8(A, e, arena);
+        smem_st_u8(((u + 1u) & ~kColBits) | col, e >> 8, arena);
+        A = ((u + (e >> 24)) & ~kColBits) | col;
+        const uint32_t np = pos + ((e >> 16) & 0xffu);
+        if ((np ^ pos) & 32u) {   // crossed a unit boundary: slide the 3-word window
+            w0 = w1;
+            w1 = w2;
+            w2 = *nxt;
+            nxt += kTileThreads;
+        }
+        pos = np;
     }
-    *st = acc;
-    return S >> 8;
+    uint32_t cnt = (((A - stage_addr) >> 10) << 2) | (A & 3u);
+    // the second symbol of the last lookup starts exactly at `stop`: it is the successor's first symbol
+    if (pos > stop && (e >> 24) == 2u) --cnt;
+    return cnt;
 }
 
 // Copy c symbols from the thread's staging words (src[0], src[stride], ...) to

@@ -71,7 +71,7 @@ struct DecodeParams {
     uint32_t *tile_counter;      // zeroed before launch
     uint64_t n_tiles;
     uint64_t *count_out;         // optional: total symbols written
-    uint32_t stage_words;        // staging words per thread
+    uint32_t stage_words;        // staging rows (one 32-bit word per thread each)
     uint32_t tile_bytes;         // output tile bytes (multiple of 16)
 };
 
@@ -89,23 +89,43 @@ struct SyncParams {
 };
 
 // =========================================================================
-// K4: decode-and-write.  One thread per 128-bit segment, kTileThreads segments
-// per tile, persistent CTAs pulling tile ids from an atomic counter so that the
-// look-back never waits on a tile that is not running.
+// K4: decode-and-write.  One thread per CHUNK of SEGS consecutive 128-bit
+// segments, kTileThreads chunks per tile, persistent CTAs pulling tile ids from
+// an atomic counter so that the look-back never waits on a tile that is not
+// running.  Per tile:
+//   load    each thread copies its chunk's units (128-bit loads) into its column
+//           of the transposed input tile (word w of thread t at [w][t])
+//   decode  decode_chunk(): flattened loop over the whole chunk, multi-symbol LUT
+//           in smem, symbols byte-stored into the thread's staging column
+//   scan    warp shuffles + 8 warp totals; warp 0 runs the decoupled look-back
+//   compact staging columns -> contiguous output tile (at the 16-byte phase of
+//           the global destination)
+//   flush   one TMA bulk store (UBLKCP) for the 16-byte aligned body, scalar
+//           stores for head/tail
 // =========================================================================
-template <bool LONG>
+__device__ __forceinline__ uint32_t gap_nibble(const uint32_t *gap_words, uint64_t j) {
+    return (__ldg(gap_words + (j >> 3)) >> (4u * (uint32_t)(j & 7))) & 15u;
+}
+
+template <int SEGS, bool LONG>
 __global__ void __launch_bounds__(kTileThreads) hd_decode_write_kernel(const DecodeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t t = threadIdx.x;
     const uint32_t lane = t & 31, warp = t >> 5;
     const uint32_t lm = p.table.lut_bits;
     const uint32_t lut_bytes = 4u << lm;
+    constexpr uint32_t kInRows = 4 * SEGS + 3;
 
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem);
-    uint8_t *s_len = smem + lut_bytes;
-    uint8_t *s_order = s_len + 256;
+    uint8_t *s_order = smem + lut_bytes;
     LongTables *s_long = reinterpret_cast<LongTables *>(s_order + 256);
-    uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem + lut_bytes + 512 + ((sizeof(LongTables) + 15) & ~15u));
+    uint32_t off = lut_bytes + (LONG ? 256u + ((uint32_t)(sizeof(LongTables) + 15) & ~15u) : 0u);
+    uint32_t *s_in = reinterpret_cast<uint32_t *>(smem + off);
+    off += kInRows * kTileThreads * 4u;
+    // the staging rows must start on a 1 KiB boundary of the shared window (see decode_chunk)
+    const uint32_t smem_abs = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t stage_abs = (smem_abs + off + 1023u) & ~1023u;
+    uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem + (stage_abs - smem_abs));
     uint8_t *s_tile = reinterpret_cast<uint8_t *>(s_stage + (size_t)p.stage_words * kTileThreads);
 
     __shared__ uint32_t s_warp_tot[kTileThreads / 32];
@@ -118,7 +138,6 @@ __global__ void __launch_bounds__(kTileThreads) hd_decode_write_kernel(const Dec
         const uint4 *src = reinterpret_cast<const uint4 *>(p.table.blob);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
         for (uint32_t i = t; i < lut_bytes / 16; i += kTileThreads) dst[i] = __ldg(src + i);
-        if (t < 64) reinterpret_cast<uint32_t *>(s_len)[t] = __ldg(reinterpret_cast<const uint32_t *>(p.table.blob + p.table.off_len) + t);
         if (LONG) {
             if (t < 64) reinterpret_cast<uint32_t *>(s_order)[t] = __ldg(reinterpret_cast<const uint32_t *>(p.table.blob + p.table.off_order) + t);
             if (t < sizeof(LongTables) / 4) reinterpret_cast<uint32_t *>(s_long)[t] = __ldg(reinterpret_cast<const uint32_t *>(p.table.blob + p.table.off_long) + t);
@@ -131,48 +150,54 @@ __global__ void __launch_bounds__(kTileThreads) hd_decode_write_kernel(const Dec
     T.lut = s_lut;
     T.idx_shift = 32 - lm;
     T.lut_bits = lm;
-    T.len_tab = s_len;
+    T.len_tab = nullptr;
     T.lt = s_long;
     T.order = s_order;
     uint32_t par = 0;
     bool store_pending = false;
+    uint32_t *const col = s_in + t;
 
     for (;;) {
         const uint64_t tile = s_tile_id[par];
         if (tile >= p.n_tiles) break;
         if (t == 0) s_tile_id[par ^ 1] = atomicAdd(p.tile_counter, 1u);   // prefetch next id
 
-        // ---------------- load this thread's segment ----------------
-        const uint64_t g = tile * kTileThreads + t;
-        const bool active = g < p.n_segments;
-        uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
-        uint32_t start = 0;
-        if (active) {
-            const uint64_t u = g * 4;
-            if (u + 4 <= p.n_units) {
-                uint4 w = __ldg(reinterpret_cast<const uint4 *>(p.units) + g);
-                r0 = w.x; r1 = w.y; r2 = w.z; r3 = w.w;
-            } else {
-                r0 = __ldg(p.units + u);
-                if (u + 1 < p.n_units) r1 = __ldg(p.units + u + 1);
-                if (u + 2 < p.n_units) r2 = __ldg(p.units + u + 2);
-            }
-            if (g == 0) start = p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit;
-            else {
-                const uint64_t j = g - 1;
-                start = (__ldg(p.gap_words + (j >> 3)) >> (4u * (uint32_t)(j & 7))) & 15u;
-            }
-        }
-        r4 = __shfl_down_sync(0xffffffffu, r0, 1);
-        if (lane == 31) {
-            const uint64_t u = (g + 1) * 4;
-            r4 = (active && u < p.n_units) ? __ldg(p.units + u) : 0u;
-        }
-
-        // ---------------- decode the segment into private staging ----------------
-        // word j of this thread lives at s_stage[j*kTileThreads + t]: bank == lane, no conflicts
+        // ---------------- load + decode this thread's chunk ----------------
+        const uint64_t g0 = (tile * kTileThreads + t) * SEGS;
         uint32_t cnt = 0;
-        if (active) cnt = decode_segment<LONG>(r0, r1, r2, r3, r4, start, T, s_stage + t, kTileThreads);
+        if (g0 < p.n_segments) {
+            const uint64_t left = p.n_segments - g0;
+            const uint32_t nseg = left < (uint64_t)SEGS ? (uint32_t)left : (uint32_t)SEGS;
+            const uint64_t u0 = g0 * 4;
+#pragma unroll
+            for (int k = 0; k < SEGS; ++k) {
+                const uint64_t u = u0 + 4u * k;
+                uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                if (u + 4 <= p.n_units) {
+                    w = __ldg(reinterpret_cast<const uint4 *>(p.units + u));
+                } else if (u < p.n_units) {
+                    w.x = __ldg(p.units + u);
+                    if (u + 1 < p.n_units) w.y = __ldg(p.units + u + 1);
+                    if (u + 2 < p.n_units) w.z = __ldg(p.units + u + 2);
+                }
+                col[(4 * k + 0) * kTileThreads] = w.x;
+                col[(4 * k + 1) * kTileThreads] = w.y;
+                col[(4 * k + 2) * kTileThreads] = w.z;
+                col[(4 * k + 3) * kTileThreads] = w.w;
+            }
+            {   // look-ahead: the first two units of the next chunk
+                const uint64_t u = u0 + 4u * SEGS;
+                uint2 w = make_uint2(0u, 0u);
+                if (u + 2 <= p.n_units) w = __ldg(reinterpret_cast<const uint2 *>(p.units + u));
+                else if (u < p.n_units) w.x = __ldg(p.units + u);
+                col[(4 * SEGS + 0) * kTileThreads] = w.x;
+                col[(4 * SEGS + 1) * kTileThreads] = w.y;
+            }
+            const uint32_t entry = g0 == 0 ? (p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit)
+                                           : gap_nibble(p.gap_words, g0 - 1);
+            const uint32_t stop = nseg * kSegmentBits + gap_nibble(p.gap_words, g0 + nseg - 1);
+            cnt = decode_chunk<LONG>(col, entry, stop, T, stage_abs + t * 4u, nullptr);
+        }
 
         // ---------------- block-wide exclusive scan of counts ----------------
         uint32_t incl = cnt;
@@ -229,8 +254,7 @@ __global__ void __launch_bounds__(kTileThreads) hd_decode_write_kernel(const Dec
                     if (p.shard_info) {
                         p.shard_info[0] = tot;
                         p.shard_info[1] = p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit;
-                        const uint64_t j = p.n_segments - 1;   // offset at which the parse leaves the shard
-                        p.shard_info[2] = (__ldg(p.gap_words + (j >> 3)) >> (4u * (uint32_t)(j & 7))) & 15u;
+                        p.shard_info[2] = gap_nibble(p.gap_words, p.n_segments - 1);   // where the parse leaves the shard
                     }
                 }
             }

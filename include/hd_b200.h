@@ -115,7 +115,10 @@ hd_status hd_decode_selfsync(const uint32_t *d_units, uint64_t n_units,
  * slicing of gpuhd/multigpu_demo.cc:178-227): the shard's first segment starts
  * at bit `first_bit` (0..15) instead of 0, and *d_count (device uint64, may be
  * NULL) receives the number of symbols written -- the one value per GPU that
- * the NCCL all-gather exchanges to place the shards' outputs. */
+ * the NCCL all-gather exchanges to place the shards' outputs.  For the gap
+ * entry n_units counts the units that may be READ and n_segments (<=
+ * ceil(n_units/4)) the segments to decode: a shard that is not the last one
+ * passes one extra unit, because its last codeword may end there. */
 hd_status hd_decode_gap_ex(const uint32_t *d_units, uint64_t n_units,
                            const uint32_t *d_gap_words, uint64_t n_segments,
                            uint32_t first_bit, const hd_table *table,
@@ -221,6 +224,9 @@ hd_status hd_selfsync_decode_host(const uint32_t *units, uint64_t n_units,
 #define HD_PROFILE_SYNC_SEAMS 1    /* K1b (both rounds) */
 #define HD_PROFILE_DECODE_WRITE 2  /* K4 */
 #define HD_PROFILE_SLOTS 4
+/* Tuning knob for benchmarks: 128-bit segments decoded per thread by the
+ * decode-and-write kernel (1, 2 or 4; 0 = automatic). */
+void hd_set_tuning(int segs_per_thread);
 /* kernels launched by this library in this process so far */
 uint64_t hd_launch_count(void);
 void hd_profile_enable(int on);

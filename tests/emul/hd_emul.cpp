@@ -64,45 +64,57 @@ struct HostSegLoader {
 
 extern "C" {
 
-// Re-enactment of hd_decode_write_kernel: tiles of kTileThreads segments, per
-// thread decode_segment -> staging, exclusive scan, clamp, compact_to_tile into
-// a tile placed at the same 16-byte phase as the kernel, copy out.
+// Re-enactment of hd_decode_write_kernel<SEGS>: tiles of kTileThreads chunks of
+// `segs` segments; per thread: transposed input column, decode_chunk -> staging
+// column (same address arithmetic as on the device, over a host arena whose
+// staging region starts on a 1 KiB boundary), exclusive scan, clamp,
+// compact_to_tile into a tile placed at the same 16-byte phase, copy out.
 int64_t emul_decode_gap(const uint32_t *units, uint64_t n_units, const uint32_t *gap_words, uint64_t n_segments,
                         uint32_t first_bit, const hd_lut_entry *flat, uint32_t flat_bits, const hd_sym_len *pairs,
-                        uint32_t n_pairs, uint8_t *out, uint64_t n_symbols, uint64_t out_addr_phase) {
+                        uint32_t n_pairs, uint8_t *out, uint64_t n_symbols, uint64_t out_addr_phase, uint32_t segs) {
     HostTables h;
     if (!make_tables(flat, flat_bits, pairs, n_pairs, h)) return -1;
+    if (segs != 1 && segs != 2 && segs != 4) return -4;
     const uint32_t min_len = h.blob.min_len ? h.blob.min_len : 1;
-    const uint32_t max_sym = (kSegmentBits + min_len - 1) / min_len;
-    const uint32_t stage_words = (max_sym + 1) / 4 + 2;
-    const uint32_t tile_bytes = ((kTileThreads * max_sym + 32) + 15) & ~15u;
-    std::vector<uint32_t> stage((size_t)stage_words * kTileThreads);
+    const uint32_t max_sym = (kSegmentBits * segs + 15 + min_len - 1) / min_len + 2;
+    const uint32_t stage_words = (max_sym + 8) / 4 + 1;
+    const uint32_t tile_sym = (kTileThreads * kSegmentBits * segs + 15 + min_len - 1) / min_len + 2;
+    const uint32_t tile_bytes = ((tile_sym + 32) + 15) & ~15u;
+    const uint32_t in_rows = 4 * segs + 3;
+    std::vector<uint32_t> in((size_t)in_rows * kTileThreads);
+    std::vector<uint8_t> arena((size_t)stage_words * kTileThreads * 4 + 2048);
+    const uint32_t stage_off = 1024;   // 1 KiB aligned offset inside the arena (device: aligned shared address)
     std::vector<uint8_t> tile(tile_bytes);
-    const uint64_t n_tiles = (n_segments + kTileThreads - 1) / kTileThreads;
+    auto nib = [&](uint64_t j) { return (gap_words[j >> 3] >> (4u * (uint32_t)(j & 7))) & 15u; };
+    const uint64_t n_chunks = (n_segments + segs - 1) / segs;
+    const uint64_t n_tiles = (n_chunks + kTileThreads - 1) / kTileThreads;
     uint64_t base = 0;
     for (uint64_t tl = 0; tl < n_tiles; ++tl) {
         // poison so that reads of never-written staging/tile bytes show up
-        std::fill(stage.begin(), stage.end(), 0xDEADBEEFu);
+        std::fill(arena.begin(), arena.end(), (uint8_t)0xDE);
         std::fill(tile.begin(), tile.end(), (uint8_t)0xEE);
+        std::fill(in.begin(), in.end(), 0xBADC0DEu);
         uint32_t cnt[kTileThreads];
         for (uint32_t t = 0; t < kTileThreads; ++t) {
-            const uint64_t g = tl * kTileThreads + t;
+            const uint64_t g0 = (tl * kTileThreads + t) * segs;
             cnt[t] = 0;
-            if (g >= n_segments) continue;
-            HostSegLoader ld{units, n_units};
-            Seg4 w = ld(g);
-            Seg4 nx = ld(g + 1);
-            uint32_t start = first_bit;
-            if (g > 0) {
-                const uint64_t j = g - 1;
-                start = (gap_words[j >> 3] >> (4u * (uint32_t)(j & 7))) & 15u;
+            if (g0 >= n_segments) continue;
+            const uint64_t left = n_segments - g0;
+            const uint32_t nseg = left < segs ? (uint32_t)left : segs;
+            uint32_t *col = in.data() + t;
+            for (uint32_t w = 0; w < 4 * segs + 2; ++w) {
+                const uint64_t u = g0 * 4 + w;
+                col[(size_t)w * kTileThreads] = u < n_units ? units[u] : 0u;
             }
-            uint32_t c = h.blob.has_long
-                             ? decode_segment<true>(w.x, w.y, w.z, w.w, nx.x, start, h.T, stage.data() + t, kTileThreads)
-                             : decode_segment<false>(w.x, w.y, w.z, w.w, nx.x, start, h.T, stage.data() + t, kTileThreads);
-            if (c > max_sym) return -2;   // staging/tile sizing assumption violated
+            const uint32_t entry = g0 == 0 ? first_bit : nib(g0 - 1);
+            const uint32_t stop = nseg * kSegmentBits + nib(g0 + nseg - 1);
+            const uint32_t sa = stage_off + t * 4u;
+            uint32_t c = h.blob.has_long ? decode_chunk<true>(col, entry, stop, h.T, sa, arena.data())
+                                         : decode_chunk<false>(col, entry, stop, h.T, sa, arena.data());
+            if (c + 2 > max_sym) return -2;   // staging/tile sizing assumption violated
             cnt[t] = c;
         }
+        const uint32_t *stage = reinterpret_cast<const uint32_t *>(arena.data() + stage_off);
         uint32_t excl = 0;
         const uint32_t A = (uint32_t)((out_addr_phase + base) & 15u);
         uint64_t tile_total = 0;
@@ -113,7 +125,7 @@ int64_t emul_decode_gap(const uint32_t *units, uint64_t n_units, const uint32_t 
             else if (my_off + c > n_symbols) c = (uint32_t)(n_symbols - my_off);
             if (c) {
                 if (A + excl + c > tile_bytes) return -3;
-                compact_to_tile(stage.data() + t, kTileThreads, c, tile.data(), A + excl);
+                compact_to_tile(stage + t, kTileThreads, c, tile.data(), A + excl);
             }
             excl += cnt[t];
             tile_total += cnt[t];

@@ -253,13 +253,14 @@ def test_sharded_gap_decode_concatenates(hd, torch_cuda):
         for rank in range(world):
             b, e = hd.shard_segments(n_seg, rank, world)
             assert b % 256 == 0
-            su = units[4 * b:min(4 * e, len(units))]
+            su = units[4 * b:min(4 * e + 1, len(units))]     # +1 unit: the shard's last codeword may end there
             sg = gaps[b // 8:]
             fb = 0 if b == 0 else int((gaps[(b - 1) >> 3] >> (4 * ((b - 1) & 7))) & 15)
             d_units = hd.to_device_units(su)
             d_gaps = torch.from_numpy(np.ascontiguousarray(sg).view(np.int32)).cuda()
             dec = hd.Decoder(d_units.numel(), selfsync=False)
-            out = dec.decode_gap(d_units, d_gaps, tab, n, first_bit=fb)    # capacity n, count tells the truth
+            out = dec.decode_gap(d_units, d_gaps, tab, n, first_bit=fb,    # capacity n, count tells the truth
+                                 n_segments=min(e, n_seg) - b)
             cnt = int(dec.count.item())
             parts.append(out[:cnt].cpu().numpy())
         whole = np.concatenate(parts)
@@ -320,12 +321,20 @@ def _sharded_selfsync(hd, units, lut, n, world, halo_segments):
     def gather():
         return np.stack([d.info.cpu().numpy() for d in decs])
 
+    # all emulated ranks step the seam protocol of sharding.resolve_seams in lockstep: the first wrong seam is
+    # repaired by its own rank from the predecessor's exact exit offset, then everybody re-gathers
     redone = []
-    for g, d in enumerate(decs):   # every emulated rank runs the same protocol; only rank g's redecode acts
-        def redecode(first_bit, d=d, g=g):
-            d._decode(first_bit=first_bit, halo=False)
-            redone.append(g)
-        placed = hd.resolve_seams(g, world, gather(), gather, redecode, n)
+    for _ in range(world):
+        cur = gather()
+        bad = hd.seams_ok(cur)
+        if not bad:
+            break
+        g = bad[0]
+        decs[g]._decode(first_bit=int(cur[g - 1][2]), halo=False)
+        redone.append(g)
+    else:
+        raise AssertionError("seams did not converge")
+    placed = hd.place_outputs([row[0] for row in gather()], n)
     parts = [d.out[:placed[g][1]].cpu().numpy() for g, d in enumerate(decs)]
     tab.close()
     return np.concatenate(parts), infos, placed, redone

@@ -14,8 +14,10 @@ ap.add_argument("--scheme", default="gap")
 ap.add_argument("--mib", type=int, default=1024)
 ap.add_argument("--r", type=float, default=0.5)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--segs", type=int, default=0)
 a = ap.parse_args()
 torch.cuda.set_device(0)
+hd.set_tuning(a.segs)
 n = a.mib << 20
 data = hd.generate(n, a.r, seed=1)
 out = torch.empty(n, dtype=torch.uint8, device="cuda")

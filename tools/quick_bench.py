@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--r", type=float, nargs="+", default=[0.5])
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--schemes", nargs="+", default=["gap", "selfsync"])
+    ap.add_argument("--segs", type=int, nargs="+", default=[0])
     a = ap.parse_args()
     torch.cuda.set_device(0)
     flush = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")
@@ -59,14 +60,24 @@ def main():
                     out = torch.empty(n, dtype=torch.uint8, device="cuda")
                     fn = lambda: dec.decode_selfsync(d_units, tab, n, out=out)
                     extra = 0
-                for _ in range(3):
+                for segs in a.segs:
+                    hd.set_tuning(segs)
+                    out.zero_()
+                    for _ in range(3):
+                        fn()
+                    torch.cuda.synchronize()
+                    ok = bool(torch.equal(out, ref))
+                    med, best = timed(fn, a.iters, flush)
+                    hd.profile_enable(True)
                     fn()
-                torch.cuda.synchronize()
-                ok = bool(torch.equal(out, ref))
-                med, best = timed(fn, a.iters, flush)
-                algo = 4 * len(units) + n + extra
-                print("%-8s %5d MiB r=%.2f ok=%s  median %.3f ms  best %.3f ms  decoded %.1f GB/s  roofline-bytes %.1f GB/s "
-                      "(gen %.1fs)" % (scheme, mib, r, ok, med, best, n / med / 1e6, algo / med / 1e6, t1 - t0), flush=True)
+                    prof = hd.profile_read()
+                    hd.profile_enable(False)
+                    algo = 4 * len(units) + n + extra
+                    print("%-8s %5d MiB r=%.2f segs=%d ok=%s  median %.3f ms  best %.3f ms  decoded %.1f GB/s  "
+                          "roofline-bytes %.1f GB/s  kernels %s" % (scheme, mib, r, segs, ok, med, best, n / med / 1e6,
+                                                                   algo / med / 1e6,
+                                                                   {k: round(v, 3) for k, v in prof.items() if v}),
+                          flush=True)
                 tab.close()
 
 
