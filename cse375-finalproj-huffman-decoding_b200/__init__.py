@@ -48,7 +48,7 @@ ABI_SYMBOLS = [
     "hd_huff_decode_host", "hd_build_code", "hd_flat_lut_from_lengths", "hd_encoded_size", "hd_encode",
     "hd_huff_write", "hd_generate", "hd_shard_segments", "hd_host_decoder_create", "hd_host_decoder_destroy",
     "hd_host_decode_selfsync", "hd_host_decode_huff", "hd_selfsync_decode_host", "hd_profile_enable",
-    "hd_profile_read", "hd_launch_count", "hd_decode_selfsync_shard", "hd_set_tuning",
+    "hd_profile_read", "hd_launch_count", "hd_decode_selfsync_shard", "hd_set_tuning", "hd_set_trace",
 ]
 PROFILE_SLOTS = ("sync_chunks", "sync_seams", "decode_write", "reserved")
 
@@ -106,8 +106,10 @@ def lib():
     L.hd_profile_enable.restype = None
     L.hd_profile_read.argtypes = [vp]
     L.hd_launch_count.restype = u64
-    L.hd_set_tuning.argtypes = [C.c_int]
+    L.hd_set_tuning.argtypes = [C.c_int, C.c_int]
     L.hd_set_tuning.restype = None
+    L.hd_set_trace.argtypes = [vp]
+    L.hd_set_trace.restype = None
     L.hd_decode_selfsync_shard.argtypes = [vp, u64, u64, u64, u32, vp, vp, u64, vp, sz, vp, vp]
     _lib = L
     return L
@@ -404,8 +406,8 @@ def profile_read():
     return dict(zip(PROFILE_SLOTS, [t[0], t[1], t[2], t[3]]))
 
 
-def set_tuning(segs_per_thread=0):
-    lib().hd_set_tuning(int(segs_per_thread))
+def set_tuning(segs_per_thread=0, threads_per_tile=0):
+    lib().hd_set_tuning(int(segs_per_thread), int(threads_per_tile))
 
 
 def launch_count():

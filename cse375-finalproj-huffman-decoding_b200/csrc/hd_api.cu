@@ -78,7 +78,7 @@ constexpr size_t kCtrlBytes = 64;
 size_t ws_bytes(uint64_t n_units, bool selfsync) {
     const uint64_t n_seg = div_up(n_units, kSegmentUnits);
     const uint64_t n_tiles = std::max<uint64_t>(1, div_up(n_seg, kTileThreads));
-    size_t b = kCtrlBytes + align_up(n_tiles * 8, 64) + kCtrlBytes;
+    size_t b = kCtrlBytes + align_up(n_tiles * 8 * kStatusStride, 64) + kCtrlBytes;
     if (selfsync) {
         const uint64_t n_chunks = std::max<uint64_t>(1, div_up(n_seg, kChunkSegs));
         const uint64_t n_blocks = div_up(n_chunks, kSyncThreads);
@@ -94,7 +94,7 @@ Workspace carve(void *ws, uint64_t n_units, bool selfsync) {
     const uint64_t n_tiles = std::max<uint64_t>(1, div_up(n_seg, kTileThreads));
     w.tile_counter = reinterpret_cast<uint32_t *>(p);
     w.tile_status = reinterpret_cast<uint64_t *>(p + kCtrlBytes);
-    w.zero_bytes = kCtrlBytes + align_up(n_tiles * 8, 64);
+    w.zero_bytes = kCtrlBytes + align_up(n_tiles * 8 * kStatusStride, 64);
     uint8_t *b = p + w.zero_bytes;
     w.changed = reinterpret_cast<uint32_t *>(b);
     w.count = reinterpret_cast<uint64_t *>(b + 48);
@@ -138,61 +138,88 @@ DeviceInfo device_info() {
     return d;
 }
 
-// K4 geometry for a table: segments per thread and the smem carve-up (must match the kernel)
+// K4 geometry for a table: decode threads per tile, segments per thread and the smem carve-up (must match the kernel)
 struct DecodeGeom {
-    int segs;
-    uint32_t stage_words, tile_bytes;
+    int nt, segs;
+    uint32_t stage_words, tile_bytes, tile_buffers;
     size_t smem;
 };
 
-DecodeGeom decode_geom(const hd_table *t, int segs) {
+DecodeGeom decode_geom(const hd_table *t, int nt, int segs, uint32_t tile_buffers) {
     DecodeGeom g;
+    g.nt = nt;
     g.segs = segs;
+    g.tile_buffers = tile_buffers;
     const uint32_t min_len = std::max<uint32_t>(1, t->host.min_len);
     // a chunk decodes bits [entry, 128*segs + next_entry), entry offsets <= 15, plus the uncounted 2nd symbol of the
     // last lookup and the always-written second byte
-    const uint32_t max_sym = (kSegmentBits * segs + 15 + min_len - 1) / min_len + 2;
-    g.stage_words = (max_sym + 8) / 4 + 1;
-    const uint32_t tile_sym = (kTileThreads * kSegmentBits * segs + 15 + min_len - 1) / min_len + 2;
+    const uint32_t max_cnt = (kSegmentBits * segs + 15 + min_len - 1) / min_len;
+    // bytes written: max_cnt symbols + the uncounted 2nd symbol + the always-written 2nd byte -> word max_cnt/4 + 1 at
+    // most; compaction reads one word past the last one holding symbols
+    g.stage_words = max_cnt / 4 + 3;
+    const uint32_t tile_sym = ((uint32_t)nt * kSegmentBits * segs + 15 + min_len - 1) / min_len + 2;
     g.tile_bytes = (uint32_t)align_up((size_t)tile_sym + 32, 16);
+    const size_t row = (size_t)nt * 4;
     g.smem = (4u << t->host.lut_bits) + (t->host.has_long ? 256 + align_up(sizeof(LongTables), 16) : 0) +
-             (size_t)(4 * segs + 3) * kTileThreads * 4 + 1024 /* staging alignment slack */ +
-             (size_t)g.stage_words * kTileThreads * 4 + g.tile_bytes;
+             (size_t)(4 * segs + 3) * row + row /* staging alignment slack */ + 2 * (size_t)g.stage_words * row +
+             (size_t)tile_buffers * g.tile_bytes;
     return g;
 }
 
-int g_force_segs = 0;   // hd_set_tuning: 0 = automatic
+unsigned long long *g_trace = nullptr;   // hd_set_trace (developer aid)
+int g_force_segs = 0, g_force_nt = 0;   // hd_set_tuning: 0 = automatic
 
 DecodeGeom pick_geom(const hd_table *t, int max_smem) {
-    if (g_force_segs == 1 || g_force_segs == 2 || g_force_segs == 4) {
-        DecodeGeom g = decode_geom(t, g_force_segs);
-        if ((int)g.smem <= max_smem) return g;
+    // two output tiles if they fit (no barrier among the decode warps), else one
+    auto fit = [&](int nt, int segs, DecodeGeom &g) {
+        g = decode_geom(t, nt, segs, 2);
+        if ((int)g.smem <= max_smem) return true;
+        g = decode_geom(t, nt, segs, 1);
+        return (int)g.smem <= max_smem;
+    };
+    DecodeGeom g;
+    if ((g_force_segs == 1 || g_force_segs == 2 || g_force_segs == 4) && (g_force_nt == 256 || g_force_nt == 512)) {
+        if (fit(g_force_nt, g_force_segs, g)) return g;
     }
-    // two segments per thread halve the look-back/barrier rate and even out the per-thread symbol counts; fall back to
-    // one when the worst-case staging (1-bit codes) would leave fewer than two CTAs per SM
-    DecodeGeom g2 = decode_geom(t, 2);
-    if (g2.smem * 2 + 2048 <= (size_t)max_smem) return g2;
-    return decode_geom(t, 1);
+    // largest tile that fits: big tiles keep the look-back chain short and amortise the per-tile work; the
+    // worst-case staging (shortest code length) decides what fits in the 227 KB of one SM
+    static const int cand[][2] = {{512, 2}, {256, 2}, {512, 1}, {256, 1}};
+    for (auto &c : cand)
+        if (fit(c[0], c[1], g)) return g;
+    return decode_geom(t, 256, 1, 1);
 }
 
 size_t sync_smem_bytes(const hd_table *t) {
     return align_up(2u << t->host.lut_bits, 16) + 256 + align_up(sizeof(LongTables), 16);
 }
 
-template <int SEGS, bool LONG>
+template <int NT, int SEGS, bool LONG>
 hd_status launch_decode(const DecodeParams &p, size_t smem, cudaStream_t s) {
-    auto kern = hd_decode_write_kernel<SEGS, LONG>;
+    auto kern = hd_decode_write_kernel<NT, SEGS, LONG>;
     HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    HD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem));
-    if (per_sm < 1) return HD_ERR_INVALID;
     const DeviceInfo di = device_info();
-    uint64_t grid = (uint64_t)di.sm_count * per_sm;   // persistent: one wave, a multiple of the SM count
+    uint64_t grid = (uint64_t)di.sm_count;   // persistent: one CTA per SM, all co-resident (the look-back spins)
     if (grid > p.n_tiles) grid = p.n_tiles;
-    kern<<<(unsigned)grid, kTileThreads, smem, s>>>(p);
+    kern<<<(unsigned)grid, NT + 32, smem, s>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     HD_CUDA(cudaGetLastError());
     return HD_OK;
+}
+
+template <bool LONG>
+hd_status launch_decode_geom(const DecodeGeom &g, const DecodeParams &p, cudaStream_t s) {
+    if (g.nt == 512) {
+        switch (g.segs) {
+            case 1: return launch_decode<512, 1, LONG>(p, g.smem, s);
+            case 2: return launch_decode<512, 2, LONG>(p, g.smem, s);
+            default: return launch_decode<512, 4, LONG>(p, g.smem, s);
+        }
+    }
+    switch (g.segs) {
+        case 1: return launch_decode<256, 1, LONG>(p, g.smem, s);
+        case 2: return launch_decode<256, 2, LONG>(p, g.smem, s);
+        default: return launch_decode<256, 4, LONG>(p, g.smem, s);
+    }
 }
 
 hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32_t *d_gap_words,
@@ -215,18 +242,15 @@ hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32
     p.tile_counter = w.tile_counter;
     const DecodeGeom g = pick_geom(table, device_info().max_smem_optin);
     if ((int)g.smem > device_info().max_smem_optin) return HD_ERR_INVALID;
-    p.n_tiles = div_up(div_up(n_segments, (uint64_t)g.segs), kTileThreads);
+    p.n_tiles = div_up(div_up(n_segments, (uint64_t)g.segs), (uint64_t)g.nt);
     p.count_out = d_count;
     p.stage_words = g.stage_words;
     p.tile_bytes = g.tile_bytes;
+    p.tile_buffers = g.tile_buffers;
+    p.trace = g_trace;
     HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes, s));
     ProfScope prof(HD_PROFILE_DECODE_WRITE, s);
-    const bool lng = table->host.has_long != 0;
-    switch (g.segs) {
-        case 1: return lng ? launch_decode<1, true>(p, g.smem, s) : launch_decode<1, false>(p, g.smem, s);
-        case 2: return lng ? launch_decode<2, true>(p, g.smem, s) : launch_decode<2, false>(p, g.smem, s);
-        default: return lng ? launch_decode<4, true>(p, g.smem, s) : launch_decode<4, false>(p, g.smem, s);
-    }
+    return table->host.has_long ? launch_decode_geom<true>(g, p, s) : launch_decode_geom<false>(g, p, s);
 }
 
 hd_status check_common(const uint32_t *d_units, uint64_t n_units, const hd_table *table, const uint8_t *d_out,
@@ -501,7 +525,11 @@ hd_status hd_decode_selfsync(const uint32_t *d_units, uint64_t n_units, const hd
 }
 
 // ------------------------------------------------------------------ tuning
-void hd_set_tuning(int segs_per_thread) { g_force_segs = segs_per_thread; }
+void hd_set_trace(void *d_buf) { g_trace = static_cast<unsigned long long *>(d_buf); }
+void hd_set_tuning(int segs_per_thread, int threads_per_tile) {
+    g_force_segs = segs_per_thread;
+    g_force_nt = threads_per_tile;
+}
 
 // ---------------------------------------------------------------- profiling
 uint64_t hd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

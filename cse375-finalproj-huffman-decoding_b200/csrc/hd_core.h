@@ -61,13 +61,28 @@ __device__ __forceinline__ void smem_st_u8(uint32_t a, uint32_t v, uint8_t *) {
 inline void smem_st_u8(uint32_t a, uint32_t v, uint8_t *arena) { arena[a] = (uint8_t)v; }
 #endif
 
-// Bits of a staging address that select the thread's column (thread t owns byte
-// lanes [4t, 4t+3] of every 1 KiB staging row: bank == lane, conflict free).
-constexpr uint32_t kColBits = (kTileThreads - 1u) << 2;
+// Staging/input tiles are TRANSPOSED: with NT decode threads per tile, thread t
+// owns byte lanes [4t, 4t+3] of every row of NT*4 bytes (bank == lane: conflict
+// free).  col_bits(NT) = the address bits that select the thread's column.
+#if defined(__CUDACC__)
+#define HD_CONSTEXPR __host__ __device__ constexpr
+#else
+#define HD_CONSTEXPR constexpr
+#endif
+HD_CONSTEXPR uint32_t col_bits(uint32_t nt) { return (nt - 1u) << 2; }
+HD_CONSTEXPR uint32_t row_shift(uint32_t nt) { return nt == 512 ? 11u : nt == 256 ? 10u : nt == 128 ? 9u : 0u; }
+
+HD_HD uint32_t byte2(uint32_t e) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(e, 0u, 0x4442u);   // one PRMT instead of shift + mask
+#else
+    return (e >> 16) & 0xffu;
+#endif
+}
 
 // Decode one chunk (SEGS consecutive 128-bit segments of one thread) in a single
 // flattened loop.  The chunk's units sit in the thread's column of the
-// transposed input tile: word w at in_col[w * kTileThreads] (conflict-free
+// transposed input tile: word w at in_col[w * NT] (conflict-free
 // refills); words past the chunk (the next chunk's first two) must be present.
 // Decoding starts at bit `entry` (< 32) and runs until the position reaches
 // `stop` = chunk bits + entry offset of the NEXT chunk, i.e. exactly to the
@@ -82,11 +97,14 @@ constexpr uint32_t kColBits = (kTileThreads - 1u) << 2;
 // "advance by n symbols" is one add plus two logic ops.  A two-symbol LUT entry
 // always stores both bytes; the second is simply overwritten by the next lookup
 // when the entry held one symbol.  Returns the number of symbols.
-template <bool LONG>
+template <int NT, bool LONG>
 HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t stop, const DecodeTables &T,
                             uint32_t stage_addr, uint8_t *arena) {
-    uint32_t w0 = in_col[0], w1 = in_col[kTileThreads], w2 = in_col[2 * kTileThreads];
-    const uint32_t *nxt = in_col + 3 * kTileThreads;
+    constexpr uint32_t kColBits = col_bits(NT);
+    static_assert(row_shift(NT) != 0, "unsupported tile width");
+    uint32_t w0 = in_col[0], w1 = in_col[NT];
+    const uint32_t *nxt = in_col + 2 * NT;
+    uint32_t w2 = *nxt;
     const uint32_t col = stage_addr & kColBits;
     uint32_t A = stage_addr;
     uint32_t pos = entry;
@@ -101,46 +119,59 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
         smem_st_u8(A, e, arena);
         smem_st_u8(((u + 1u) & ~kColBits) | col, e >> 8, arena);
         A = ((u + (e >> 24)) & ~kColBits) | col;
-        const uint32_t np = pos + ((e >> 16) & 0xffu);
-        if ((np ^ pos) & 32u) {   // crossed a unit boundary: slide the 3-word window
+        const uint32_t np = pos + byte2(e);
+        if ((np ^ pos) & 32u) {   // crossed a unit boundary: slide the window
             w0 = w1;
             w1 = w2;
-            w2 = *nxt;
-            nxt += kTileThreads;
+            nxt += NT;
         }
+        // unconditional (re)load of the word after the window: issued a whole iteration before the slide that
+        // consumes it, so its latency never sits on the loop-carried path
+        w2 = *nxt;
         pos = np;
     }
-    uint32_t cnt = (((A - stage_addr) >> 10) << 2) | (A & 3u);
+    uint32_t cnt = (((A - stage_addr) >> row_shift(NT)) << 2) | (A & 3u);
     // the second symbol of the last lookup starts exactly at `stop`: it is the successor's first symbol
     if (pos > stop && (e >> 24) == 2u) --cnt;
     return cnt;
 }
 
-// Copy c symbols from the thread's staging words (src[0], src[stride], ...) to
-// byte offset D of the CTA's output tile.  Interior words are written as whole
-// 32-bit stores, the (at most two) words shared with neighbouring threads byte
-// by byte.
+// lower 32 bits of (hi:lo) >> (s & 31)
+HD_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    s &= 31u;
+    return s ? ((lo >> s) | (hi << (32u - s))) : lo;
+#endif
+}
+
+// Copy c symbols from the thread's staging column (word m at src[m * stride],
+// little-endian bytes) to byte offset D of the CTA's output tile: up to three
+// head bytes until the destination is word aligned, whole 32-bit words through
+// one funnel shift each, up to three tail bytes.  Reads at most one staging word
+// past the last one that holds symbols.
 HD_HD void compact_to_tile(const uint32_t *src, uint32_t stride, uint32_t c, uint8_t *tile, uint32_t D) {
-    const uint32_t delta = D & 3u;
-    const uint32_t sh = delta * 8u;
-    const uint32_t D0 = D & ~3u;
-    uint32_t *dst32 = reinterpret_cast<uint32_t *>(tile + D0);
-    const uint32_t total = delta + c;
-    const uint32_t nw = (total + 3u) >> 2;
-    uint32_t prev = 0;
-    for (uint32_t m = 0; m < nw; ++m) {
-        const uint32_t cur = src[(size_t)m * stride];
-        const uint32_t v = funnel_l(prev, cur, sh);
-        prev = cur;
-        const uint32_t lo_b = (m == 0) ? delta : 0u;
-        const uint32_t rem = total - 4u * m;
-        const uint32_t hi_b = rem < 4u ? rem : 4u;
-        if (lo_b == 0 && hi_b == 4) {
-            dst32[m] = v;
-        } else {
-            uint8_t *d8 = tile + D0 + 4u * m;
-            for (uint32_t b = lo_b; b < hi_b; ++b) d8[b] = (uint8_t)(v >> (8u * b));
-        }
+    uint32_t w = src[0];
+    uint32_t head = (4u - (D & 3u)) & 3u;
+    if (head > c) head = c;
+    for (uint32_t i = 0; i < head; ++i) tile[D + i] = (uint8_t)(w >> (8u * i));
+    uint32_t rem = c - head;
+    if (rem == 0) return;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(tile + D + head);
+    const uint32_t sh = 8u * head;
+    const uint32_t *nx = src + stride;
+    while (rem >= 4u) {
+        const uint32_t n = *nx;
+        *dst++ = funnel_r(w, n, sh);
+        w = n;
+        nx += stride;
+        rem -= 4u;
+    }
+    if (rem) {
+        const uint32_t v = funnel_r(w, *nx, sh);
+        uint8_t *d8 = reinterpret_cast<uint8_t *>(dst);
+        for (uint32_t i = 0; i < rem; ++i) d8[i] = (uint8_t)(v >> (8u * i));
     }
 }
 

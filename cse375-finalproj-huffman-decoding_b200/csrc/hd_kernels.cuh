@@ -32,6 +32,18 @@ __device__ __forceinline__ uint64_t ld_relaxed_gpu_u64(const uint64_t *p) {
 __device__ __forceinline__ void st_relaxed_gpu_u64(uint64_t *p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_release_cta_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+// order-independent publication of a tile status: a PREFIX word (flag 2) always beats an AGGREGATE word (flag 1)
+__device__ __forceinline__ void red_max_gpu_u64(uint64_t *p, uint64_t v) {
+    asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 // TMA bulk store shared::cta -> global (SASS: UBLKCP); 16-byte aligned, size % 16 == 0
 __device__ __forceinline__ void tma_bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
@@ -48,6 +60,9 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 constexpr uint64_t kFlagAggregate = 1ull << 62;   // tile aggregate published
 constexpr uint64_t kFlagPrefix = 2ull << 62;      // inclusive prefix published
 constexpr uint64_t kFlagMask = 3ull << 62;
+// One status word per 32-byte sector: every scan warp reads the statuses of the ~#SMs tiles in flight below its own,
+// so densely packed words turn a few L2 lines into a hot spot (measured: ~2.5 us per 256-word poll).
+constexpr uint32_t kStatusStride = 4;   // in 64-bit words
 
 struct TableDev {
     const uint8_t *blob;      // device copy of TableBlob::bytes
@@ -73,7 +88,15 @@ struct DecodeParams {
     uint64_t *count_out;         // optional: total symbols written
     uint32_t stage_words;        // staging rows (one 32-bit word per thread each)
     uint32_t tile_bytes;         // output tile bytes (multiple of 16)
+    uint32_t tile_buffers;       // 2: tiles of consecutive steps alternate (no decode-warp barrier); 1: one barrier per step
+    unsigned long long *trace;   // optional (hd_set_trace): per-step timestamps of CTA kTraceCta, 8 u64 per step
 };
+constexpr uint32_t kTraceCta = 5, kTraceSteps = 48;
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 struct SyncParams {
     const uint32_t *units;
@@ -89,164 +112,171 @@ struct SyncParams {
 };
 
 // =========================================================================
-// K4: decode-and-write.  One thread per CHUNK of SEGS consecutive 128-bit
-// segments, kTileThreads chunks per tile, persistent CTAs pulling tile ids from
-// an atomic counter so that the look-back never waits on a tile that is not
-// running.  Per tile:
-//   load    each thread copies its chunk's units (128-bit loads) into its column
-//           of the transposed input tile (word w of thread t at [w][t])
-//   decode  decode_chunk(): flattened loop over the whole chunk, multi-symbol LUT
-//           in smem, symbols byte-stored into the thread's staging column
-//   scan    warp shuffles + 8 warp totals; warp 0 runs the decoupled look-back
-//   compact staging columns -> contiguous output tile (at the 16-byte phase of
-//           the global destination)
-//   flush   one TMA bulk store (UBLKCP) for the 16-byte aligned body, scalar
-//           stores for head/tail
+// K4: decode-and-write.  ONE persistent CTA per SM: NT decode threads (one per
+// CHUNK of SEGS consecutive 128-bit segments; NT chunks = one tile) plus one
+// scan warp.  Tile ids come from an atomic ticket counter so that the look-back
+// never waits on a tile that is not running.  The CTA is software pipelined over
+// two staging buffers so that the L2 round trips of the decoupled look-back are
+// hidden behind the decode of the next tile:
+//
+//   decode warps, step k:   load + decode tile k -> staging[k&1]   (decode_chunk)
+//                           warp-scan the symbol counts, arrive FULL[k&1]
+//                           wait READY[(k-1)&1]  (prefix of tile k-1, long done)
+//                           compact staging[(k-1)&1] -> output tile, flush it
+//                           (one TMA bulk store, SASS UBLKCP, + scalar head/tail)
+//   scan warp, step k:      take the ticket for step k+2; wait FULL[k&1]; scan
+//                           the warp totals; publish the tile aggregate; look
+//                           back over predecessors' aggregates/prefixes (64-bit
+//                           flagged words, ld/st.relaxed.gpu); publish the
+//                           inclusive prefix; arrive READY[k&1]
+//
+// FULL/READY are named barriers (bar.arrive / bar.sync): the only CTA-wide
+// synchronisation per tile besides one barrier among the decode warps between
+// compaction and flush.
 // =========================================================================
 __device__ __forceinline__ uint32_t gap_nibble(const uint32_t *gap_words, uint64_t j) {
     return (__ldg(gap_words + (j >> 3)) >> (4u * (uint32_t)(j & 7))) & 15u;
 }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t n) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+constexpr uint32_t kBarFull = 1, kBarReady = 3, kBarDecode = 5;
 
-template <int SEGS, bool LONG>
-__global__ void __launch_bounds__(kTileThreads) hd_decode_write_kernel(const DecodeParams p) {
+// Decoupled look-back, 256 predecessors per round (8 per lane, nearest first).
+// All CTAs of the persistent grid work on neighbouring tiles at the same time, so
+// the nearest published PREFIX is typically one "generation" (~#SMs tiles) back:
+// a 32-wide window would need ~5 serial L2 round trips per tile, this needs one.
+// Only slots nearer than the nearest prefix are waited for.
+__device__ __forceinline__ uint64_t lookback_wide(const uint64_t *status, uint64_t tile, uint32_t lane, uint32_t *polls = nullptr) {
+    uint64_t excl = 0;
+    uint32_t n_polls = 0;
+    int64_t hi = (int64_t)tile - 1;
+    for (;;) {
+        const int64_t first = hi - 8 * (int64_t)lane;
+        ++n_polls;
+        uint64_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t idx = first - j;
+            v[j] = idx >= 0 ? ld_relaxed_gpu_u64(status + idx * kStatusStride) : kFlagPrefix;   // virtual tile -1: prefix 0
+        }
+        uint64_t sum = 0;
+        uint32_t state = 0;   // 0: aggregates only, 1: reached a prefix, 2: reached an unpublished slot first
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (state == 0) {
+                const uint64_t f = v[j] & kFlagMask;
+                if (f == 0) {
+                    state = 2;
+                } else {
+                    sum += v[j] & ~kFlagMask;
+                    if (f == kFlagPrefix) state = 1;
+                }
+            }
+        }
+        const uint32_t m_found = __ballot_sync(0xffffffffu, state == 1);
+        const uint32_t m_wait = __ballot_sync(0xffffffffu, state == 2);
+        const uint32_t stop_lane = m_found ? (uint32_t)__ffs(m_found) - 1u : 32u;
+        const uint32_t upto = stop_lane >= 31u ? 0xffffffffu : ((2u << stop_lane) - 1u);   // lanes 0..stop_lane
+        if (m_wait & upto) continue;   // something nearer than the nearest prefix is not published yet: poll again
+        uint64_t c = (lane <= stop_lane) ? sum : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        excl += c;
+        if (m_found) break;
+        hi -= 256;
+    }
+    if (polls) *polls = n_polls;
+    return excl;
+}
+
+template <int NT, int SEGS, bool LONG>
+__global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const DecodeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
+    constexpr uint32_t kNW = NT / 32;
+    constexpr uint32_t kRowBytes = NT * 4;
+    constexpr uint32_t kInRows = 4 * SEGS + 3;
     const uint32_t t = threadIdx.x;
     const uint32_t lane = t & 31, warp = t >> 5;
     const uint32_t lm = p.table.lut_bits;
     const uint32_t lut_bytes = 4u << lm;
-    constexpr uint32_t kInRows = 4 * SEGS + 3;
 
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem);
     uint8_t *s_order = smem + lut_bytes;
     LongTables *s_long = reinterpret_cast<LongTables *>(s_order + 256);
     uint32_t off = lut_bytes + (LONG ? 256u + ((uint32_t)(sizeof(LongTables) + 15) & ~15u) : 0u);
     uint32_t *s_in = reinterpret_cast<uint32_t *>(smem + off);
-    off += kInRows * kTileThreads * 4u;
-    // the staging rows must start on a 1 KiB boundary of the shared window (see decode_chunk)
+    off += kInRows * kRowBytes;
+    // staging rows must start on a row-size boundary of the shared window (see decode_chunk)
     const uint32_t smem_abs = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t stage_abs = (smem_abs + off + 1023u) & ~1023u;
-    uint32_t *s_stage = reinterpret_cast<uint32_t *>(smem + (stage_abs - smem_abs));
-    uint8_t *s_tile = reinterpret_cast<uint8_t *>(s_stage + (size_t)p.stage_words * kTileThreads);
+    const uint32_t stage_abs = (smem_abs + off + kRowBytes - 1u) & ~(kRowBytes - 1u);
+    const uint32_t stage_buf_bytes = p.stage_words * kRowBytes;
+    uint8_t *s_stage = smem + (stage_abs - smem_abs);
+    uint8_t *s_tile = s_stage + 2u * stage_buf_bytes;   // two output tiles of p.tile_bytes each
 
-    __shared__ uint32_t s_warp_tot[kTileThreads / 32];
-    __shared__ uint32_t s_tile_id[2];
-    __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_wtot[2][kNW];   // warp totals of the tile in buffer b; the scan warp turns them into exclusive offsets
+    __shared__ uint32_t s_tileid[3];   // ring: tile of step k in slot k % 3 (taken by decode thread 0 one step ahead)
+    __shared__ unsigned long long s_base[2];
+    __shared__ uint32_t s_total[2];
+    __shared__ uint32_t s_sum[2], s_arrived[2];   // tile total / number of warps that added theirs
+    __shared__ uint32_t s_ready[2];               // s_ready[b] = k+1 once the prefix of step k (buffer b) is in s_base[b]
 
     // ---- stage the tables once per CTA (persistent) ----
+    if (t < 2) { s_sum[t] = 0; s_arrived[t] = 0; s_ready[t] = 0; }
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.table.blob);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-        for (uint32_t i = t; i < lut_bytes / 16; i += kTileThreads) dst[i] = __ldg(src + i);
+        for (uint32_t i = t; i < lut_bytes / 16; i += NT + 32) dst[i] = __ldg(src + i);
         if (LONG) {
             if (t < 64) reinterpret_cast<uint32_t *>(s_order)[t] = __ldg(reinterpret_cast<const uint32_t *>(p.table.blob + p.table.off_order) + t);
             if (t < sizeof(LongTables) / 4) reinterpret_cast<uint32_t *>(s_long)[t] = __ldg(reinterpret_cast<const uint32_t *>(p.table.blob + p.table.off_long) + t);
         }
     }
-    if (t == 0) s_tile_id[0] = atomicAdd(p.tile_counter, 1u);
+    if (t == NT) {
+        s_tileid[0] = atomicAdd(p.tile_counter, 1u);
+        s_tileid[1] = atomicAdd(p.tile_counter, 1u);
+    }
     __syncthreads();
 
-    DecodeTables T;
-    T.lut = s_lut;
-    T.idx_shift = 32 - lm;
-    T.lut_bits = lm;
-    T.len_tab = nullptr;
-    T.lt = s_long;
-    T.order = s_order;
-    uint32_t par = 0;
-    bool store_pending = false;
-    uint32_t *const col = s_in + t;
-
-    for (;;) {
-        const uint64_t tile = s_tile_id[par];
-        if (tile >= p.n_tiles) break;
-        if (t == 0) s_tile_id[par ^ 1] = atomicAdd(p.tile_counter, 1u);   // prefetch next id
-
-        // ---------------- load + decode this thread's chunk ----------------
-        const uint64_t g0 = (tile * kTileThreads + t) * SEGS;
-        uint32_t cnt = 0;
-        if (g0 < p.n_segments) {
-            const uint64_t left = p.n_segments - g0;
-            const uint32_t nseg = left < (uint64_t)SEGS ? (uint32_t)left : (uint32_t)SEGS;
-            const uint64_t u0 = g0 * 4;
-#pragma unroll
-            for (int k = 0; k < SEGS; ++k) {
-                const uint64_t u = u0 + 4u * k;
-                uint4 w = make_uint4(0u, 0u, 0u, 0u);
-                if (u + 4 <= p.n_units) {
-                    w = __ldg(reinterpret_cast<const uint4 *>(p.units + u));
-                } else if (u < p.n_units) {
-                    w.x = __ldg(p.units + u);
-                    if (u + 1 < p.n_units) w.y = __ldg(p.units + u + 1);
-                    if (u + 2 < p.n_units) w.z = __ldg(p.units + u + 2);
-                }
-                col[(4 * k + 0) * kTileThreads] = w.x;
-                col[(4 * k + 1) * kTileThreads] = w.y;
-                col[(4 * k + 2) * kTileThreads] = w.z;
-                col[(4 * k + 3) * kTileThreads] = w.w;
-            }
-            {   // look-ahead: the first two units of the next chunk
-                const uint64_t u = u0 + 4u * SEGS;
-                uint2 w = make_uint2(0u, 0u);
-                if (u + 2 <= p.n_units) w = __ldg(reinterpret_cast<const uint2 *>(p.units + u));
-                else if (u < p.n_units) w.x = __ldg(p.units + u);
-                col[(4 * SEGS + 0) * kTileThreads] = w.x;
-                col[(4 * SEGS + 1) * kTileThreads] = w.y;
-            }
-            const uint32_t entry = g0 == 0 ? (p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit)
-                                           : gap_nibble(p.gap_words, g0 - 1);
-            const uint32_t stop = nseg * kSegmentBits + gap_nibble(p.gap_words, g0 + nseg - 1);
-            cnt = decode_chunk<LONG>(col, entry, stop, T, stage_abs + t * 4u, nullptr);
-        }
-
-        // ---------------- block-wide exclusive scan of counts ----------------
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (uint32_t)d) incl += v;
-        }
-        if (lane == 31) s_warp_tot[warp] = incl;
-        __syncthreads();   // (B)
-
-        // ---------------- decoupled look-back (warp 0) ----------------
-        if (warp == 0) {
-            uint32_t wt = lane < kTileThreads / 32 ? s_warp_tot[lane] : 0;
+    if (t >= NT) {
+        // ======================= scan warp =======================
+        for (uint32_t k = 0;; ++k) {
+            const uint32_t b = k & 1u;
+            // (slot k % 3 was written by decode thread 0 during step k-1 and is not rewritten before step k+2)
+            const uint64_t tile = s_tileid[k % 3u];
+            if (tile >= p.n_tiles) break;
+            named_bar_sync(kBarFull + b, NT + 32);
+            // ticket of step k+2 (steps 0 and 1 got theirs in the prologue).  Issued here so that the atomic's
+            // round trip overlaps the look-back, but no earlier: a tile must not be claimed long before it is
+            // decoded, or every higher tile's look-back waits for it.
+            uint32_t ticket = 0;
+            if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u);
+            const bool tr = p.trace && blockIdx.x == kTraceCta && k < kTraceSteps && lane == 0;
+            if (tr) p.trace[k * 8 + 4] = gtime_ns();
+            const uint32_t wt = lane < kNW ? s_wtot[b][lane] : 0u;
             uint32_t wi = wt;
 #pragma unroll
-            for (int d = 1; d < kTileThreads / 32; d <<= 1) {
+            for (int d = 1; d < (int)kNW; d <<= 1) {
                 uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
                 if (lane >= (uint32_t)d) wi += v;
             }
-            if (lane < kTileThreads / 32) s_warp_tot[lane] = wi - wt;   // exclusive warp offsets
-            const uint64_t agg = __shfl_sync(0xffffffffu, wi, kTileThreads / 32 - 1);
-            if (lane == 0) st_relaxed_gpu_u64(p.tile_status + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | agg);
+            if (lane < kNW) s_wtot[b][lane] = wi - wt;   // exclusive warp offsets
+            const uint64_t agg = __shfl_sync(0xffffffffu, wi, kNW - 1);
+            // (the tile AGGREGATE was already published by the last decode warp to finish, so that it never waits
+            // behind this warp's look-back of the previous tile)
             uint64_t excl = 0;
             if (tile > 0) {
-                int64_t look = (int64_t)tile - 1;
-                for (;;) {
-                    const int64_t idx = look - lane;
-                    uint64_t v = kFlagPrefix;   // virtual tile -1: prefix 0
-                    if (idx >= 0) {
-                        do { v = ld_relaxed_gpu_u64(p.tile_status + idx); } while ((v & kFlagMask) == 0);
-                    }
-                    const uint32_t pm = __ballot_sync(0xffffffffu, (v & kFlagMask) == kFlagPrefix);
-                    // lanes at or before the nearest prefix contribute
-                    const uint32_t first = pm ? (uint32_t)__ffs(pm) - 1 : 32u;
-                    uint64_t c = (lane <= first) ? (v & ~kFlagMask) : 0ull;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-                    excl += c;
-                    if (pm) break;
-                    look -= 32;
-                }
-                if (lane == 0) st_relaxed_gpu_u64(p.tile_status + tile, kFlagPrefix | (excl + agg));
+                uint32_t polls = 0;
+                excl = lookback_wide(p.tile_status, tile, lane, &polls);
+                if (tr) p.trace[k * 8 + 2] = polls;
+                if (lane == 0) red_max_gpu_u64(p.tile_status + tile * kStatusStride, kFlagPrefix | (excl + agg));
             }
             if (lane == 0) {
-                s_base = excl;
-                s_total = (uint32_t)agg;
-                // the previous tile's TMA store must have finished READING s_tile
-                if (store_pending) tma_bulk_wait_read0();
+                s_base[b] = excl;
+                s_total[b] = (uint32_t)agg;
                 if (tile + 1 == p.n_tiles) {
                     uint64_t tot = excl + agg;
                     tot = tot < p.n_symbols ? tot : p.n_symbols;
@@ -258,55 +288,172 @@ __global__ void __launch_bounds__(kTileThreads) hd_decode_write_kernel(const Dec
                     }
                 }
             }
+            if (tr) { p.trace[k * 8 + 5] = gtime_ns(); p.trace[k * 8 + 6] = tile; }
+            // slot (k+2)%3 held step k-1's tile, which nobody reads any more
+            if (lane == 0) s_tileid[(k + 2u) % 3u] = ticket;
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) st_release_cta_u32(&s_ready[b], k + 1u);
         }
-        __syncthreads();   // (C)
+        return;
+    }
 
-        // ---------------- compact staging -> output tile ----------------
-        const uint64_t base = s_base;
-        const uint32_t excl_t = s_warp_tot[warp] + incl - cnt;
-        // clamp to n_symbols (pad bits decode to garbage: reference clamps with
-        // out_pos < next_out_pos, cuhd_gpu_decoder.cu:101-105)
-        uint64_t my_off = base + excl_t;
-        uint32_t c = cnt;
-        if (my_off >= p.n_symbols) c = 0;
-        else if (my_off + c > p.n_symbols) c = (uint32_t)(p.n_symbols - my_off);
-        const uint32_t A = (uint32_t)((reinterpret_cast<uintptr_t>(p.out) + base) & 15u);
-        if (c) compact_to_tile(s_stage + t, kTileThreads, c, s_tile, A + excl_t);
-        fence_proxy_async_smem();
-        __syncthreads();   // (D)
+    // ======================= decode warps =======================
+    DecodeTables T;
+    T.lut = s_lut;
+    T.idx_shift = 32 - lm;
+    T.lut_bits = lm;
+    T.len_tab = nullptr;
+    T.lt = s_long;
+    T.order = s_order;
+    uint32_t *const col = s_in + t;
+    bool store_pending = false, prev_valid = false;
+    uint32_t prev_cnt = 0, prev_incl = 0;
 
-        // ---------------- flush the tile: TMA bulk body + scalar head/tail ----------------
-        {
-            uint64_t tot = s_total;   // symbols of this tile, clamped to n_symbols below
-            uint64_t lim = base >= p.n_symbols ? 0 : p.n_symbols - base;
-            if (tot > lim) tot = lim;
-            const uint32_t total = (uint32_t)tot;
-            uint32_t head = (16u - A) & 15u;
+    // Inputs of the NEXT tile are prefetched into registers while the previous tile is compacted and flushed,
+    // so that the DRAM latency of the unit loads is off the critical path of a step.
+    uint4 pf_w[SEGS];
+    uint2 pf_la = make_uint2(0u, 0u);
+    uint32_t pf_entry = 0, pf_stop = 0;   // pf_stop == 0: this thread has no chunk in the tile
+    auto prefetch = [&](uint64_t tile) {
+        pf_stop = 0;
+        if (tile >= p.n_tiles) return;
+        const uint64_t g0 = (tile * NT + t) * SEGS;
+        if (g0 >= p.n_segments) return;
+        const uint64_t left = p.n_segments - g0;
+        const uint32_t nseg = left < (uint64_t)SEGS ? (uint32_t)left : (uint32_t)SEGS;
+        const uint64_t u0 = g0 * 4;
+#pragma unroll
+        for (int q = 0; q < SEGS; ++q) {
+            const uint64_t u = u0 + 4u * q;
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            if (u + 4 <= p.n_units) {
+                w = __ldg(reinterpret_cast<const uint4 *>(p.units + u));
+            } else if (u < p.n_units) {
+                w.x = __ldg(p.units + u);
+                if (u + 1 < p.n_units) w.y = __ldg(p.units + u + 1);
+                if (u + 2 < p.n_units) w.z = __ldg(p.units + u + 2);
+            }
+            pf_w[q] = w;
+        }
+        {   // look-ahead: the first two units of the next chunk
+            const uint64_t u = u0 + 4u * SEGS;
+            uint2 w = make_uint2(0u, 0u);
+            if (u + 2 <= p.n_units) w = __ldg(reinterpret_cast<const uint2 *>(p.units + u));
+            else if (u < p.n_units) w.x = __ldg(p.units + u);
+            pf_la = w;
+        }
+        pf_entry = g0 == 0 ? (p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit) : gap_nibble(p.gap_words, g0 - 1);
+        pf_stop = nseg * kSegmentBits + gap_nibble(p.gap_words, g0 + nseg - 1);
+    };
+    prefetch(s_tileid[0]);
+
+    for (uint32_t k = 0;; ++k) {
+        const uint32_t b = k & 1u;
+        const uint64_t tile = s_tileid[k % 3u];
+        const bool valid = tile < p.n_tiles;
+        uint32_t cnt = 0, incl = 0;
+        const bool tr = p.trace && blockIdx.x == kTraceCta && k < kTraceSteps && t == 0;
+        if (tr) p.trace[k * 8 + 0] = gtime_ns();
+        if (valid) {
+            // ---------------- decode this thread's chunk (units were prefetched) ----------------
+            if (pf_stop) {
+#pragma unroll
+                for (int q = 0; q < SEGS; ++q) {
+                    col[(4 * q + 0) * NT] = pf_w[q].x;
+                    col[(4 * q + 1) * NT] = pf_w[q].y;
+                    col[(4 * q + 2) * NT] = pf_w[q].z;
+                    col[(4 * q + 3) * NT] = pf_w[q].w;
+                }
+                col[(4 * SEGS + 0) * NT] = pf_la.x;
+                col[(4 * SEGS + 1) * NT] = pf_la.y;
+                if (tr) p.trace[k * 8 + 7] = gtime_ns();
+                cnt = decode_chunk<NT, LONG>(col, pf_entry, pf_stop, T, stage_abs + b * stage_buf_bytes + t * 4u, nullptr);
+            }
+            // ---------------- warp-wide inclusive scan of the counts ----------------
+            incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += v;
+            }
+            // this warp's TMA store of two steps ago read the tile buffer that is written again next step
+            if (store_pending) { tma_bulk_wait_read0(); store_pending = false; }
+            if (lane == 31) {
+                s_wtot[b][warp] = incl;
+                // the last warp to finish publishes the tile aggregate right away (tile 0: it is its own prefix)
+                atomicAdd(&s_sum[b], incl);
+                __threadfence_block();
+                if (atomicAdd(&s_arrived[b], 1u) == kNW - 1) {
+                    const uint32_t total = atomicExch(&s_sum[b], 0u);
+                    s_arrived[b] = 0;
+                    red_max_gpu_u64(p.tile_status + tile * kStatusStride, (tile == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)total);
+                }
+            }
+            __threadfence_block();
+            if (tr) p.trace[k * 8 + 1] = gtime_ns();
+            named_bar_arrive(kBarFull + b, NT + 32);
+        }
+        if (prev_valid) {
+            if (p.tile_buffers == 1u) {
+                // single output tile: every warp's TMA store of the previous step must have finished reading it
+                // before any warp compacts into it again
+                if (store_pending) { tma_bulk_wait_read0(); store_pending = false; }
+                named_bar_sync(kBarDecode, NT);
+            }
+            // wait for the scan warp's prefix of tile k-1 (computed while we decoded tile k): a flag, not a
+            // barrier, so that with two output tiles no decode warp ever waits for another decode warp
+            while (ld_acquire_cta_u32(&s_ready[b ^ 1u]) < k) {}
+        }
+        if (valid) prefetch(s_tileid[(k + 1u) % 3u]);   // from the prologue or published with s_ready above
+        if (prev_valid) {
+            // ---------------- finish tile k-1: compact this WARP's symbols and flush them ----------------
+            const uint32_t pb = b ^ 1u;
+            const uint64_t base = s_base[pb];
+            const uint32_t woff = s_wtot[pb][warp];                            // this warp's offset in the tile
+            const uint32_t wtot = __shfl_sync(0xffffffffu, prev_incl, 31);     // this warp's symbols
+            const uint32_t excl_t = woff + prev_incl - prev_cnt;
+            // clamp to n_symbols (pad bits decode to garbage: reference clamps with
+            // out_pos < next_out_pos, cuhd_gpu_decoder.cu:101-105)
+            const uint64_t my_off = base + excl_t;
+            uint32_t c = prev_cnt;
+            if (my_off >= p.n_symbols) c = 0;
+            else if (my_off + c > p.n_symbols) c = (uint32_t)(p.n_symbols - my_off);
+            const uint32_t A = (uint32_t)((reinterpret_cast<uintptr_t>(p.out) + base) & 15u);
+            uint8_t *tile_buf = s_tile + (p.tile_buffers == 2u ? pb * p.tile_bytes : 0u);
+            if (c) compact_to_tile(reinterpret_cast<const uint32_t *>(s_stage + pb * stage_buf_bytes) + t, NT, c, tile_buf, A + excl_t);
+            fence_proxy_async_smem();
+            __syncwarp();
+            // flush: the warp's span is contiguous in the tile and in the output, and both have the same 16-byte
+            // phase -> one TMA bulk store for the aligned body, lanes 0-15 / 16-31 for head / tail bytes
+            const uint64_t wbase = base + woff;
+            uint64_t lim = wbase >= p.n_symbols ? 0 : p.n_symbols - wbase;
+            const uint32_t total = wtot < lim ? wtot : (uint32_t)lim;
+            const uint8_t *sp = tile_buf + A + woff;
+            uint8_t *gp = p.out + wbase;
+            uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(gp) & 15u)) & 15u;
             if (head > total) head = total;
             const uint32_t body = (total - head) & ~15u;
             const uint32_t tail = total - head - body;
-            uint8_t *gout = p.out + base;
-            if (t == 0) {
-                if (body) {
-                    tma_bulk_store(gout + head, s_tile + A + head, body);
-                    tma_bulk_commit();
-                    store_pending = true;
-                } else {
-                    store_pending = false;
-                }
+            if (lane == 0 && body) {
+                tma_bulk_store(gp + head, sp + head, body);
+                tma_bulk_commit();
+                store_pending = true;
             }
-            if (t >= 32 && t < 48) {
-                const uint32_t i = t - 32;
-                if (i < head) gout[i] = s_tile[A + i];
-            } else if (t >= 64 && t < 80) {
-                const uint32_t i = t - 64;
-                if (i < tail) gout[head + body + i] = s_tile[A + head + body + i];
+            if (lane < 16) {
+                if (lane < head) gp[lane] = sp[lane];
+            } else {
+                const uint32_t i = lane - 16;
+                if (i < tail) gp[head + body + i] = sp[head + body + i];
             }
         }
-        par ^= 1;
-        // the next iteration reads s_tile_id[par] written before barrier (B)
+        if (tr) p.trace[k * 8 + 3] = gtime_ns();
+        if (!valid) break;
+        prev_valid = true;
+        prev_cnt = cnt;
+        prev_incl = incl;
     }
-    if (t == 0 && store_pending) tma_bulk_wait0();
+    if (store_pending) tma_bulk_wait0();
 }
 
 // =========================================================================

@@ -224,9 +224,13 @@ hd_status hd_selfsync_decode_host(const uint32_t *units, uint64_t n_units,
 #define HD_PROFILE_SYNC_SEAMS 1    /* K1b (both rounds) */
 #define HD_PROFILE_DECODE_WRITE 2  /* K4 */
 #define HD_PROFILE_SLOTS 4
-/* Tuning knob for benchmarks: 128-bit segments decoded per thread by the
- * decode-and-write kernel (1, 2 or 4; 0 = automatic). */
-void hd_set_tuning(int segs_per_thread);
+/* Tuning knob for benchmarks: 128-bit segments decoded per thread (1, 2 or 4)
+ * and decode threads per tile (256 or 512) of the decode-and-write kernel;
+ * 0, 0 = automatic (largest tile that fits the SM's shared memory). */
+void hd_set_tuning(int segs_per_thread, int threads_per_tile);
+/* Developer aid: device buffer (48 x 8 u64) that receives per-step %globaltimer
+ * stamps of one CTA of the decode-and-write kernel; NULL switches it off. */
+void hd_set_trace(void *d_buf);
 /* kernels launched by this library in this process so far */
 uint64_t hd_launch_count(void);
 void hd_profile_enable(int on);

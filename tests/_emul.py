@@ -30,7 +30,8 @@ def lib():
         L = C.CDLL(build())
         L.emul_decode_gap.restype = C.c_int64
         L.emul_decode_gap.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p,
-                                      C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32]
+                                      C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
+                                      C.c_uint32]
         L.emul_sync.restype = C.c_int64
         L.emul_sync.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                 C.c_void_p, C.c_void_p]
@@ -48,10 +49,11 @@ def _tbl(flat_lut, pairs):
     return None, None, 0, p, p.ctypes.data, p.shape[0]
 
 
-def decode_gap(units, gap_words, n_segments, n_symbols, flat_lut=None, pairs=None, first_bit=0, phase=0, segs=None):
-    if segs is None:   # exercise every chunk geometry the kernel is instantiated for
-        res = [decode_gap(units, gap_words, n_segments, n_symbols, flat_lut, pairs, first_bit, phase, s)
-               for s in (1, 2, 4)]
+def decode_gap(units, gap_words, n_segments, n_symbols, flat_lut=None, pairs=None, first_bit=0, phase=0, segs=None,
+               nt=256):
+    if segs is None:   # exercise every tile geometry the kernel is instantiated for
+        res = [decode_gap(units, gap_words, n_segments, n_symbols, flat_lut, pairs, first_bit, phase, s, n)
+               for s, n in ((1, 256), (2, 256), (4, 256), (1, 512), (2, 512))]
         assert all(np.array_equal(res[0], r) for r in res[1:]), "chunk geometries disagree"
         return res[0]
     units = np.ascontiguousarray(units, dtype=np.uint32)
@@ -59,7 +61,7 @@ def decode_gap(units, gap_words, n_segments, n_symbols, flat_lut=None, pairs=Non
     f, fp, fb, p, pp, npairs = _tbl(flat_lut, pairs)
     out = np.zeros(n_symbols + 64, dtype=np.uint8)
     got = lib().emul_decode_gap(units.ctypes.data, len(units), gw.ctypes.data, n_segments, first_bit, fp, fb, pp,
-                                npairs, out.ctypes.data, n_symbols, phase, segs)
+                                npairs, out.ctypes.data, n_symbols, phase, segs, nt)
     if got < 0:
         raise RuntimeError("emul_decode_gap failed: %d" % got)
     return out[:got]

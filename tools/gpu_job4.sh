@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 120 python tools/prof_target.py --scheme gap --mib 16 --reps 2 > gpurun_out/smoke4.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke4.log
+timeout 600 python -m pytest tests -m gpu -x -q --timeout 120 > gpurun_out/r1_pytest4.log 2>&1; echo "pytest rc=$?"
+tail -4 gpurun_out/r1_pytest4.log
+timeout 300 python tools/quick_bench.py --mib 100 1024 --r 0.5 --iters 10 --geom 2,512 4,256 2,256 1,256 2>&1 | tee gpurun_out/r1_quick4.log

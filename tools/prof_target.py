@@ -15,9 +15,10 @@ ap.add_argument("--mib", type=int, default=1024)
 ap.add_argument("--r", type=float, default=0.5)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--segs", type=int, default=0)
+ap.add_argument("--nt", type=int, default=0)
 a = ap.parse_args()
 torch.cuda.set_device(0)
-hd.set_tuning(a.segs)
+hd.set_tuning(a.segs, a.nt)
 n = a.mib << 20
 data = hd.generate(n, a.r, seed=1)
 out = torch.empty(n, dtype=torch.uint8, device="cuda")

@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--r", type=float, nargs="+", default=[0.5])
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--schemes", nargs="+", default=["gap", "selfsync"])
-    ap.add_argument("--segs", type=int, nargs="+", default=[0])
+    ap.add_argument("--geom", nargs="+", default=["0,0"], help="segs,nt pairs (0,0 = automatic)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     flush = torch.zeros(256 << 20, dtype=torch.uint8, device="cuda")
@@ -60,8 +60,9 @@ def main():
                     out = torch.empty(n, dtype=torch.uint8, device="cuda")
                     fn = lambda: dec.decode_selfsync(d_units, tab, n, out=out)
                     extra = 0
-                for segs in a.segs:
-                    hd.set_tuning(segs)
+                for geom in a.geom:
+                    segs, nt = map(int, geom.split(","))
+                    hd.set_tuning(segs, nt)
                     out.zero_()
                     for _ in range(3):
                         fn()
@@ -73,8 +74,8 @@ def main():
                     prof = hd.profile_read()
                     hd.profile_enable(False)
                     algo = 4 * len(units) + n + extra
-                    print("%-8s %5d MiB r=%.2f segs=%d ok=%s  median %.3f ms  best %.3f ms  decoded %.1f GB/s  "
-                          "roofline-bytes %.1f GB/s  kernels %s" % (scheme, mib, r, segs, ok, med, best, n / med / 1e6,
+                    print("%-8s %5d MiB r=%.2f geom=%s ok=%s  median %.3f ms  best %.3f ms  decoded %.1f GB/s  "
+                          "roofline-bytes %.1f GB/s  kernels %s" % (scheme, mib, r, geom, ok, med, best, n / med / 1e6,
                                                                    algo / med / 1e6,
                                                                    {k: round(v, 3) for k, v in prof.items() if v}),
                           flush=True)
