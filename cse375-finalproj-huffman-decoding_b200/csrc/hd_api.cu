@@ -61,15 +61,15 @@ inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 // ---- workspace layout -------------------------------------------------------
 // [ctrl A: 64 B {tile_counter u32}] [tile_status: n_tiles u64]   <- zeroed per K4 launch
 // [ctrl B: 64 B {changed[8] u32, count u64}]                      <- zeroed per self-sync call
-// [gap words (self-sync only): n_chunks u32]
-// [blk_entry (self-sync only): n_sync_blocks u8]
+// [gap words (self-sync only): 2 x n_chunks u32]
+// [cur_entry (self-sync only): n_chunks u8]
 struct Workspace {
     uint32_t *tile_counter;
     uint64_t *tile_status;
     uint32_t *changed;       // 8 counters
     uint64_t *count;
     uint32_t *gap_words;
-    uint8_t *blk_entry;
+    uint8_t *blk_entry;      // per sync chunk: entry offset its landings were parsed from
     size_t zero_bytes;       // prefix of the workspace that must be zeroed per K4 launch
 };
 
@@ -80,9 +80,8 @@ size_t ws_bytes(uint64_t n_units, bool selfsync) {
     const uint64_t n_tiles = std::max<uint64_t>(1, div_up(n_seg, kTileThreads));
     size_t b = kCtrlBytes + align_up(n_tiles * 8 * kStatusStride, 64) + kCtrlBytes;
     if (selfsync) {
-        const uint64_t n_chunks = std::max<uint64_t>(1, div_up(n_seg, kChunkSegs));
-        const uint64_t n_blocks = div_up(n_chunks, kSyncThreads);
-        b += align_up(n_chunks * 4, 64) + align_up(n_blocks, 64);
+        const uint64_t n_chunks = std::max<uint64_t>(1, div_up(n_seg, kSyncChunkSegs));
+        b += align_up(n_chunks * (kSyncChunkSegs / 8) * 4, 64) + align_up(n_chunks, 64);
     }
     return b;
 }
@@ -101,9 +100,9 @@ Workspace carve(void *ws, uint64_t n_units, bool selfsync) {
     w.gap_words = nullptr;
     w.blk_entry = nullptr;
     if (selfsync) {
-        const uint64_t n_chunks = std::max<uint64_t>(1, div_up(n_seg, kChunkSegs));
+        const uint64_t n_chunks = std::max<uint64_t>(1, div_up(n_seg, kSyncChunkSegs));
         w.gap_words = reinterpret_cast<uint32_t *>(b + kCtrlBytes);
-        w.blk_entry = b + kCtrlBytes + align_up(n_chunks * 4, 64);
+        w.blk_entry = b + kCtrlBytes + align_up(n_chunks * (kSyncChunkSegs / 8) * 4, 64);
     }
     return w;
 }
@@ -263,6 +262,107 @@ hd_status check_common(const uint32_t *d_units, uint64_t n_units, const hd_table
     return HD_OK;
 }
 
+// phases 1+2: build the gap array of a stream by self-synchronisation
+struct SyncLaunch {
+    SyncParams p;
+    size_t smem_tables, smem_parse;
+    bool exact, lng;
+};
+
+SyncLaunch make_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit, const hd_table *table,
+                            uint32_t *d_gap_words, uint8_t *d_cur_entry, uint32_t *d_ctrl, uint64_t n_units_readable,
+                            bool exact) {
+    SyncLaunch L;
+    SyncParams &p = L.p;
+    p.units = d_units;
+    p.n_units = n_units_readable > n_units ? n_units_readable : n_units;
+    p.n_segments = div_up(n_units, kSegmentUnits);
+    p.n_chunks = div_up(p.n_segments, kSyncChunkSegs);
+    p.n_tiles = div_up(p.n_chunks, 32);
+    p.first_bit = first_bit;
+    p.table = table_dev(table);
+    p.gap_words = d_gap_words;
+    p.cur_entry = d_cur_entry;
+    p.changed = d_ctrl;
+    p.tile_counter = d_ctrl + 8;
+    L.smem_tables = sync_smem_bytes(table);
+    L.smem_parse = L.smem_tables + (size_t)kSyncWarps * kSyncTileBytes;
+    L.exact = exact;
+    L.lng = table->host.has_long != 0;
+    return L;
+}
+
+template <bool EXACT, bool LONG>
+hd_status launch_sync_parse(const SyncLaunch &L, cudaStream_t s) {
+    auto kern = hd_sync_parse_kernel<EXACT, LONG>;
+    HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_parse));
+    uint64_t grid = (uint64_t)device_info().sm_count;   // persistent: one CTA per SM, warps pull tiles
+    const uint64_t need = div_up(L.p.n_tiles, kSyncWarps);
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, kSyncWarps * 32, L.smem_parse, s>>>(L.p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+template <bool EXACT, bool LONG>
+hd_status launch_sync_walk(const SyncLaunch &L, uint32_t *changed, cudaStream_t s) {
+    SyncParams p = L.p;
+    p.changed = changed;
+    auto kern = hd_sync_walk_kernel<EXACT, LONG>;
+    HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_tables));
+    const unsigned grid = (unsigned)div_up(div_up(p.n_chunks, kSyncWalkChunks), 128);
+    kern<<<grid, 128, L.smem_tables, s>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+#define HD_SYNC_DISPATCH(fn, L, ...)                                                               \
+    ((L).exact ? ((L).lng ? fn<true, true>((L), __VA_ARGS__) : fn<true, false>((L), __VA_ARGS__))   \
+               : ((L).lng ? fn<false, true>((L), __VA_ARGS__) : fn<false, false>((L), __VA_ARGS__)))
+
+// K1a + two K1b rounds: the first repairs chunk heads whose halo was too short, the second picks up the few group
+// seams whose predecessor's exit moved and otherwise only verifies (changed[1] == 0 <=> fixed point reached).  d_ctrl must be zeroed (kCtrlBytes) before.
+hd_status run_sync(const SyncLaunch &L, cudaStream_t s) {
+    {
+        ProfScope prof(HD_PROFILE_SYNC_CHUNKS, s);
+        hd_status st = HD_SYNC_DISPATCH(launch_sync_parse, L, s);
+        if (st != HD_OK) return st;
+    }
+    if (L.p.n_chunks > 1) {
+        ProfScope prof(HD_PROFILE_SYNC_SEAMS, s);
+        for (int round = 0; round < 2; ++round) {
+            hd_status st = HD_SYNC_DISPATCH(launch_sync_walk, L, L.p.changed + round, s);
+            if (st != HD_OK) return st;
+        }
+    }
+    return HD_OK;
+}
+
+// further rounds until no chunk exit changes (host loop of the reference: cuhd_gpu_decoder.cu:461-495); only
+// reached for codes that fail to synchronise inside a whole 2048-bit chunk.
+hd_status finish_sync(const SyncLaunch &L, cudaStream_t s, bool *extra_rounds) {
+    *extra_rounds = false;
+    if (L.p.n_chunks <= 1) return HD_OK;
+    uint32_t h_changed = 0;
+    HD_CUDA(cudaMemcpyAsync(&h_changed, L.p.changed + 1, 4, cudaMemcpyDeviceToHost, s));
+    HD_CUDA(cudaStreamSynchronize(s));
+    if (h_changed == 0) return HD_OK;
+    *extra_rounds = true;
+    uint32_t *changed = L.p.changed + 2;
+    const uint64_t max_rounds = div_up(L.p.n_chunks, kSyncWalkChunks) + 2;
+    for (uint64_t round = 0; round <= max_rounds; ++round) {
+        HD_CUDA(cudaMemsetAsync(changed, 0, 4, s));
+        hd_status st = HD_SYNC_DISPATCH(launch_sync_walk, L, changed, s);
+        if (st != HD_OK) return st;
+        HD_CUDA(cudaMemcpyAsync(&h_changed, changed, 4, cudaMemcpyDeviceToHost, s));
+        HD_CUDA(cudaStreamSynchronize(s));
+        if (h_changed == 0) return HD_OK;
+    }
+    return HD_ERR_UNRESOLVED;
+}
+
 }  // namespace
 
 extern "C" {
@@ -356,86 +456,6 @@ hd_status hd_decode_gap(const uint32_t *d_units, uint64_t n_units, const uint32_
                             workspace_bytes, nullptr, stream);
 }
 
-// phases 1+2: build the gap array of a stream by self-synchronisation
-static hd_status run_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit, const hd_table *table,
-                          uint32_t *d_gap_words, uint8_t *d_blk_entry, uint32_t *d_changed, cudaStream_t s,
-                          uint64_t n_units_readable = 0) {
-    SyncParams p;
-    p.units = d_units;
-    p.n_units = n_units_readable > n_units ? n_units_readable : n_units;
-    p.n_segments = div_up(n_units, kSegmentUnits);
-    p.n_chunks = div_up(p.n_segments, kChunkSegs);
-    p.n_blocks = div_up(p.n_chunks, kSyncThreads);
-    p.first_bit = first_bit;
-    p.table = table_dev(table);
-    p.gap_words = d_gap_words;
-    p.blk_entry = d_blk_entry;
-    p.changed = d_changed;
-    const size_t smem = sync_smem_bytes(table);
-    HD_CUDA(cudaFuncSetAttribute(hd_sync_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HD_CUDA(cudaFuncSetAttribute(hd_sync_seams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-        ProfScope prof(HD_PROFILE_SYNC_CHUNKS, s);
-        hd_sync_chunks_kernel<<<(unsigned)p.n_blocks, kSyncThreads, smem, s>>>(p);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-    }
-    HD_CUDA(cudaGetLastError());
-    if (p.n_blocks > 1) {
-        ProfScope prof(HD_PROFILE_SYNC_SEAMS, s);
-        // two seam rounds up front: the first repairs the heads of the blocks,
-        // the second only verifies (changed[1] == 0 <=> fixed point reached)
-        const unsigned grid = (unsigned)div_up(p.n_blocks - 1, kSyncThreads);
-        for (int round = 0; round < 2; ++round) {
-            p.changed = d_changed + round;
-            hd_sync_seams_kernel<<<grid, kSyncThreads, smem, s>>>(p);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            HD_CUDA(cudaGetLastError());
-        }
-    }
-    return HD_OK;
-}
-
-// further seam rounds until no block exit changes (host loop of the reference:
-// cuhd_gpu_decoder.cu:461-495); only reached for codes that fail to
-// synchronise inside a whole 128-chunk block.
-static hd_status finish_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit, const hd_table *table,
-                             uint32_t *d_gap_words, uint8_t *d_blk_entry, uint32_t *d_changed, cudaStream_t s,
-                             bool *extra_rounds, uint64_t n_units_readable = 0) {
-    *extra_rounds = false;
-    const uint64_t n_segments = div_up(n_units, kSegmentUnits);
-    const uint64_t n_chunks = div_up(n_segments, kChunkSegs);
-    const uint64_t n_blocks = div_up(n_chunks, kSyncThreads);
-    if (n_blocks <= 1) return HD_OK;
-    uint32_t h_changed = 0;
-    HD_CUDA(cudaMemcpyAsync(&h_changed, d_changed + 1, 4, cudaMemcpyDeviceToHost, s));
-    HD_CUDA(cudaStreamSynchronize(s));
-    if (h_changed == 0) return HD_OK;
-    *extra_rounds = true;
-    SyncParams p;
-    p.units = d_units;
-    p.n_units = n_units_readable > n_units ? n_units_readable : n_units;
-    p.n_segments = n_segments;
-    p.n_chunks = n_chunks;
-    p.n_blocks = n_blocks;
-    p.first_bit = first_bit;
-    p.table = table_dev(table);
-    p.gap_words = d_gap_words;
-    p.blk_entry = d_blk_entry;
-    p.changed = d_changed + 2;
-    const size_t smem = sync_smem_bytes(table);
-    const unsigned grid = (unsigned)div_up(n_blocks - 1, kSyncThreads);
-    for (uint64_t round = 0; round <= n_blocks; ++round) {
-        HD_CUDA(cudaMemsetAsync(p.changed, 0, 4, s));
-        hd_sync_seams_kernel<<<grid, kSyncThreads, smem, s>>>(p);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        HD_CUDA(cudaGetLastError());
-        HD_CUDA(cudaMemcpyAsync(&h_changed, p.changed, 4, cudaMemcpyDeviceToHost, s));
-        HD_CUDA(cudaStreamSynchronize(s));
-        if (h_changed == 0) return HD_OK;
-    }
-    return HD_ERR_UNRESOLVED;
-}
-
 hd_status hd_selfsync_gap_array(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit,
                                 const hd_table *table, uint32_t *d_gap_words_out, void *d_workspace,
                                 size_t workspace_bytes, void *stream) {
@@ -447,10 +467,12 @@ hd_status hd_selfsync_gap_array(const uint32_t *d_units, uint64_t n_units, uint3
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Workspace w = carve(d_workspace, n_units, true);
     HD_CUDA(cudaMemsetAsync(w.changed, 0, kCtrlBytes, s));
-    st = run_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, s);
+    // exact landings: this entry returns a gap array in the .huff sense (first codeword of every segment)
+    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, true);
+    st = run_sync(L, s);
     if (st != HD_OK) return st;
     bool extra = false;
-    st = finish_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, s, &extra);
+    st = finish_sync(L, s, &extra);
     if (st != HD_OK) return st;
     const uint64_t n_seg = div_up(n_units, kSegmentUnits);
     // chunk words are exactly the .huff gap words (8 nibbles each); the last
@@ -473,12 +495,13 @@ hd_status hd_decode_selfsync_ex(const uint32_t *d_units, uint64_t n_units, uint3
     // K1a + K1b x2, then K4 speculatively; the convergence flag is read once at
     // the end (the reference reads flags after every phase-2 launch, :461-495)
     HD_CUDA(cudaMemsetAsync(w.changed, 0, kCtrlBytes, s));
-    st = run_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, s);
+    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, false);
+    st = run_sync(L, s);
     if (st != HD_OK) return st;
     st = run_gap_decode(d_units, n_units, w.gap_words, n_seg, first_bit, table, d_out, n_symbols, w, d_count, s);
     if (st != HD_OK) return st;
     bool extra = false;
-    st = finish_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, s, &extra);
+    st = finish_sync(L, s, &extra);
     if (st != HD_OK) return st;
     if (extra)   // the speculative K4 ran on an unconverged gap array: redo it
         st = run_gap_decode(d_units, n_units, w.gap_words, n_seg, first_bit, table, d_out, n_symbols, w, d_count, s);
@@ -498,20 +521,20 @@ hd_status hd_decode_selfsync_shard(const uint32_t *d_units, uint64_t n_units_hal
     hd_status st = check_common(d_units, n_units, table, d_out, out_cap, d_workspace);
     if (st != HD_OK) return st;
     if (n_units_shard == 0 || first_bit > 15) return HD_ERR_INVALID;
-    if (n_units_halo % (kSegmentUnits * kChunkSegs)) return HD_ERR_INVALID;   // gap words must line up
+    if (n_units_halo % (kSegmentUnits * 8)) return HD_ERR_INVALID;   // gap words (8 segments each) must line up
     if (n_units_readable < n_units) n_units_readable = n_units;
     if (workspace_bytes < ws_bytes(n_units, true)) return HD_ERR_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Workspace w = carve(d_workspace, n_units, true);
     HD_CUDA(cudaMemsetAsync(w.changed, 0, kCtrlBytes, s));
-    st = run_sync(d_units, n_units, n_units_halo ? 0u : first_bit, table, w.gap_words, w.blk_entry, w.changed, s,
-                  n_units_readable);
+    const SyncLaunch L = make_sync(d_units, n_units, n_units_halo ? 0u : first_bit, table, w.gap_words, w.blk_entry,
+                                   w.changed, n_units_readable, false);
+    st = run_sync(L, s);
     if (st != HD_OK) return st;
     bool extra = false;
-    st = finish_sync(d_units, n_units, n_units_halo ? 0u : first_bit, table, w.gap_words, w.blk_entry, w.changed, s,
-                     &extra, n_units_readable);
+    st = finish_sync(L, s, &extra);
     if (st != HD_OK) return st;
-    const uint64_t halo_words = n_units_halo / (kSegmentUnits * kChunkSegs);
+    const uint64_t halo_words = n_units_halo / (kSegmentUnits * 8);
     const uint32_t *gaps = w.gap_words + halo_words;
     return run_gap_decode(d_units + n_units_halo, n_units_shard, gaps, div_up(n_units_shard, kSegmentUnits), first_bit,
                           table, d_out, out_cap, w, nullptr, s, n_units_readable - n_units_halo,

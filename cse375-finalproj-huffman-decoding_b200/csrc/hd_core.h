@@ -182,54 +182,75 @@ struct SyncLut {
     uint32_t lm;
     const LongTables *lt;
     const uint8_t *order;
-    bool has_long;
 };
 
 struct Seg4 {
     uint32_t x, y, z, w;
 };
 
-// Parse chunk `chunk` (kChunkSegs segments) starting at bit offset `entry` of
-// its first segment and record, in nibble k of the returned word, the offset at
-// which the parse enters segment 8*chunk+k+1.  With check=true the parse stops
-// as soon as such an offset equals the one already recorded in `word`: the two
-// parses have merged and are identical from there on (the reference tests the
-// same condition, cuhd_gpu_decoder.cu:208-213).  LoadSeg(s) returns the four
-// units of segment s (zeros past the end of the stream).
-template <typename LoadSeg>
-HD_HD uint32_t sync_parse_chunk(LoadSeg load_seg, uint64_t chunk, uint32_t entry, const SyncLut &L, bool check,
-                                uint32_t word, bool &merged) {
-    const uint64_t seg0 = chunk * kChunkSegs;
-    Seg4 cur = load_seg(seg0);
-    Seg4 nxt = load_seg(seg0 + 1);
-    uint32_t off = entry;
-    merged = false;
-    for (uint32_t k = 0; k < kChunkSegs; ++k) {
-        uint32_t r0 = cur.x, r1 = cur.y, r2 = cur.z, r3 = cur.w, r4 = nxt.x;
-        uint32_t pos = off;
-        do {
-            const uint32_t win = funnel_l(r1, r0, pos);
-            uint32_t ent = L.lut[win >> L.idx_shift];
-            uint32_t first = ent >> 8;
-            if (L.has_long && first == 0) {
-                first = (resolve_long(win, L.lm, L.lt, L.order) >> 16) & 0xffu;
+// Parse ONE 128-bit segment held in r0..r3 (+ r4 = first unit of the next
+// segment) from bit `pos` (< 32) and return the offset, relative to the start
+// of the NEXT segment, at which the parse lands there ("landing", 0..15).
+//
+// The sync LUT entry holds {jump, first}: jump = total length of all complete
+// codewords inside the LUT window, first = length of the first one.
+//   EXACT = false: always take the whole jump.  The landing is then a codeword
+//     boundary of this parse at or after the segment end, but not necessarily
+//     the FIRST one (a jump may skip over a codeword that starts exactly at the
+//     boundary).  Because every parse uses the same table, two parses that have
+//     merged still produce identical landings, which is all synchronisation
+//     needs; and the decode kernel stops a chunk exactly at the landing recorded
+//     for its successor, so such a gap array decodes to the same bytes.
+//   EXACT = true: a jump that would pass the segment end is replaced by single
+//     codeword steps, so that the landing is the offset of the FIRST codeword
+//     starting in the next segment -- the .huff gap-array definition
+//     (encoder.cu:307-312), needed by hd_selfsync_gap_array.
+// Merge test of the reference: cuhd_gpu_decoder.cu:208-213.
+template <bool EXACT, bool LONG>
+HD_HD uint32_t sync_segment(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t pos,
+                            const SyncLut &L) {
+    while (pos < kSegmentBits) {
+        const uint32_t win = funnel_l(r1, r0, pos);
+        uint32_t ent = L.lut[win >> L.idx_shift];
+        if (LONG) {
+            if (ent == 0) {
+                const uint32_t first = (resolve_long(win, L.lm, L.lt, L.order) >> 16) & 0xffu;
                 ent = first | (first << 8);
             }
-            const uint32_t jump = ent & 0xffu;
-            // a multi-code jump is only safe while it cannot pass the segment end
-            const uint32_t step = (pos + jump <= kSegmentBits) ? jump : first;
-            const uint32_t np = pos + step;
-            if ((np ^ pos) & 32u) { r0 = r1; r1 = r2; r2 = r3; r3 = r4; }
-            pos = np;
-        } while (pos < kSegmentBits);
-        off = pos - kSegmentBits;
-        const uint32_t shift = 4u * k;
-        if (check && ((word >> shift) & 15u) == off) { merged = true; break; }
-        word = (word & ~(15u << shift)) | (off << shift);
+        }
+        uint32_t step = ent & 0xffu;
+        if (EXACT) {
+            if (pos + step > kSegmentBits) step = ent >> 8;
+        }
+        const uint32_t np = pos + step;
+        if ((np ^ pos) & 32u) { r0 = r1; r1 = r2; r2 = r3; r3 = r4; }
+        pos = np;
+    }
+    return pos - kSegmentBits;
+}
+
+// Repair step (K1b): re-parse chunk `chunk` (kSyncChunkSegs segments) from the
+// exact entry offset `entry` and overwrite the recorded landings until the new
+// parse lands where the recorded one did (the parses have merged and are
+// identical from there on).  words[0..1] = the chunk's two gap words.  Returns
+// true if the parses merged inside the chunk; false means the chunk's exit
+// changed and the next chunk has to be looked at again.
+template <bool EXACT, bool LONG, typename LoadSeg>
+HD_HD bool sync_repair_chunk(LoadSeg load_seg, uint64_t chunk, uint32_t entry, const SyncLut &L, uint32_t words[2]) {
+    const uint64_t seg0 = chunk * kSyncChunkSegs;
+    Seg4 cur = load_seg(seg0);
+    Seg4 nxt = load_seg(seg0 + 1);
+    uint32_t pos = entry;
+    for (uint32_t k = 0; k < kSyncChunkSegs; ++k) {
+        pos = sync_segment<EXACT, LONG>(cur.x, cur.y, cur.z, cur.w, nxt.x, pos, L);
+        const uint32_t shift = 4u * (k & 7u);
+        uint32_t &word = words[k >> 3];
+        if (((word >> shift) & 15u) == pos) return true;
+        word = (word & ~(15u << shift)) | (pos << shift);
         cur = nxt;
         nxt = load_seg(seg0 + k + 2);
     }
-    return word;
+    return false;
 }
 
 }  // namespace hd

@@ -19,8 +19,12 @@ constexpr uint32_t kMaxLutBits = 12;     // primary multi-symbol LUT index width
 constexpr uint32_t kMaxCodeLen = 16;     // .huff MAX_CODEWORD_LENGTH (decoder/include/constants.hpp:5)
 
 // ---- geometry of the synchronisation kernels (K1a/K1b) --------------------
-constexpr uint32_t kChunkSegs = 8;       // segments per sync thread (= one gap word)
-constexpr uint32_t kSyncThreads = 128;   // chunks per sync block
+constexpr uint32_t kSyncChunkSegs = 16;  // segments per sync thread (2048 bits = two gap words)
+constexpr uint32_t kSyncHaloSegs = 4;    // segments parsed speculatively BEFORE the chunk (512 bits)
+constexpr uint32_t kSyncWarps = 24;      // warps per persistent sync CTA (one CTA per SM)
+constexpr uint32_t kSyncTileSegs = 32 * kSyncChunkSegs;                   // segments per warp tile
+constexpr uint32_t kSyncTileUnits16 = kSyncHaloSegs + kSyncTileSegs + 1;  // 16-byte units staged per warp tile
+constexpr uint32_t kSyncTileBytes = (kSyncTileUnits16 + kSyncTileUnits16 / 16 + 2) * 16;   // + 1 pad unit per 16
 
 // Host description of a prefix code: code/len indexed by symbol value.
 struct HostCode {

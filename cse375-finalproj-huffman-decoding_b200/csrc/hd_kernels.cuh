@@ -102,13 +102,14 @@ struct SyncParams {
     const uint32_t *units;
     uint64_t n_units;            // units that may be READ
     uint64_t n_segments;
-    uint64_t n_chunks;           // ceil(n_segments / kChunkSegs)
-    uint64_t n_blocks;           // ceil(n_chunks / kSyncThreads)
+    uint64_t n_chunks;           // ceil(n_segments / kSyncChunkSegs)
+    uint64_t n_tiles;            // warp tiles: ceil(n_chunks / 32)
     uint32_t first_bit;
     TableDev table;
-    uint32_t *gap_words;         // out: one word per chunk
-    uint8_t *blk_entry;          // per sync block: entry offset its chunk 0 assumed
-    uint32_t *changed;           // per-round "some block exit changed" counter
+    uint32_t *gap_words;         // out: two words per chunk (nibble k of word w = landing into segment 8w+k+1)
+    uint8_t *cur_entry;          // per chunk: the entry offset its recorded landings were parsed from
+    uint32_t *changed;           // per-round "some chunk's exit changed" counter
+    uint32_t *tile_counter;      // ticket counter of the persistent K1a warps (zeroed before launch)
 };
 
 // =========================================================================
@@ -314,9 +315,11 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
     // so that the DRAM latency of the unit loads is off the critical path of a step.
     uint4 pf_w[SEGS];
     uint2 pf_la = make_uint2(0u, 0u);
-    uint32_t pf_entry = 0, pf_stop = 0;   // pf_stop == 0: this thread has no chunk in the tile
+    // raw gap words + nibble shifts; the nibbles are extracted when the step starts so that the prefetch itself
+    // never waits for a load.  pf_bits == 0: this thread has no chunk in the tile.
+    uint32_t pf_gw0 = 0, pf_gw1 = 0, pf_sh = 0, pf_bits = 0;
     auto prefetch = [&](uint64_t tile) {
-        pf_stop = 0;
+        pf_bits = 0;
         if (tile >= p.n_tiles) return;
         const uint64_t g0 = (tile * NT + t) * SEGS;
         if (g0 >= p.n_segments) return;
@@ -343,8 +346,17 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             else if (u < p.n_units) w.x = __ldg(p.units + u);
             pf_la = w;
         }
-        pf_entry = g0 == 0 ? (p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit) : gap_nibble(p.gap_words, g0 - 1);
-        pf_stop = nseg * kSegmentBits + gap_nibble(p.gap_words, g0 + nseg - 1);
+        const uint64_t j1 = g0 + nseg - 1;   // gap element = entry offset of the NEXT chunk
+        pf_gw1 = __ldg(p.gap_words + (j1 >> 3));
+        uint32_t sh0 = 0;
+        if (g0 == 0) {
+            pf_gw0 = p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit;
+        } else {
+            pf_gw0 = __ldg(p.gap_words + ((g0 - 1) >> 3));
+            sh0 = 4u * (uint32_t)((g0 - 1) & 7);
+        }
+        pf_sh = sh0 | (4u * (uint32_t)(j1 & 7)) << 8;
+        pf_bits = nseg * kSegmentBits;
     };
     prefetch(s_tileid[0]);
 
@@ -357,7 +369,9 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
         if (tr) p.trace[k * 8 + 0] = gtime_ns();
         if (valid) {
             // ---------------- decode this thread's chunk (units were prefetched) ----------------
-            if (pf_stop) {
+            if (pf_bits) {
+                const uint32_t pf_entry = (pf_gw0 >> (pf_sh & 31u)) & 15u;
+                const uint32_t pf_stop = pf_bits + ((pf_gw1 >> (pf_sh >> 8)) & 15u);
 #pragma unroll
                 for (int q = 0; q < SEGS; ++q) {
                     col[(4 * q + 0) * NT] = pf_w[q].x;
@@ -403,7 +417,7 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             }
             // wait for the scan warp's prefix of tile k-1 (computed while we decoded tile k): a flag, not a
             // barrier, so that with two output tiles no decode warp ever waits for another decode warp
-            while (ld_acquire_cta_u32(&s_ready[b ^ 1u]) < k) {}
+            while (ld_acquire_cta_u32(&s_ready[b ^ 1u]) < k) __nanosleep(64);
         }
         if (valid) prefetch(s_tileid[(k + 1u) % 3u]);   // from the prologue or published with s_ready above
         if (prev_valid) {
@@ -457,9 +471,29 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
 }
 
 // =========================================================================
-// K1: synchronisation.  A "chunk" is kChunkSegs consecutive 128-bit segments;
-// its result is one gap word: nibble k = bit offset at which the parse enters
-// segment 8c+k+1 (nibble 7 = exit of the chunk = entry of chunk c+1).
+// K1: synchronisation = building the gap array of a stream whose codeword
+// boundaries are unknown (replaces phases 1+2 of CUHD, cuhd_gpu_decoder.cu:
+// 145-327, and its host loop :461-495).
+//
+// K1a  one thread per CHUNK of 16 segments.  The thread starts parsing 4
+//      segments (512 bits) BEFORE its chunk from bit 0 of that halo: by the time
+//      it reaches its own chunk the parse has, with high probability, merged
+//      with the true one (mean self-synchronisation distance of generate.cpp
+//      data at redundancy 0.5: 324 bits), so every landing it records inside its
+//      chunk is final.  One full-speed pass with all lanes busy; no block-level
+//      fixed-point iteration.  It also records the offset at which its parse
+//      entered the chunk (cur_entry).
+// K1b  one thread per group of 32 chunks walks the group's seams: if the
+//      predecessor's landing into a chunk differs from the entry the chunk's
+//      landings were parsed from, re-parse the chunk head from the exact entry
+//      until the parses merge (sync_repair_chunk).  Sparse and short.  Rounds
+//      repeat until no group exit changes: a code that never self-synchronises
+//      degrades to a sequential chain instead of producing garbage.
+//
+// K1a is persistent: one CTA per SM, every WARP pulls tiles of 32 chunks from an
+// atomic counter and stages its tile's units with 16-byte cp.async into a
+// private, padded (one pad unit per 16: conflict-free LDS.128 per quarter warp)
+// shared-memory region -- coalesced global reads, no block barrier at all.
 // =========================================================================
 // loads the four units of segment s (zeros past the end of the stream)
 struct GlobalSegLoader {
@@ -506,73 +540,164 @@ __device__ __forceinline__ void sync_stage_tables(const TableDev &tb, uint8_t *s
     L.lm = lm;
     L.lt = s_long;
     L.order = s_order;
-    L.has_long = tb.has_long != 0;
+}
+__device__ __forceinline__ uint32_t sync_tables_bytes(uint32_t lut_bits) {
+    return (((2u << lut_bits) + 15u) & ~15u) + 256u + (((uint32_t)sizeof(LongTables) + 15u) & ~15u);
 }
 
-// K1a: every thread parses its chunk speculatively from bit 0, then the block
-// iterates "take the predecessor's exit, re-parse until the parses merge" until
-// nothing changes (intra-block fixed point; ballot/barrier-or detects it).
-__global__ void __launch_bounds__(kSyncThreads) hd_sync_chunks_kernel(const SyncParams p) {
+// 16-byte async copy global -> shared (LDGSTS), zero-filling the bytes past src_bytes
+__device__ __forceinline__ void cp_async16_zfill(void *sdst, const void *gsrc, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// loads the four units of (global) segment s from a warp's staged, padded tile that starts at segment q0
+struct TileSegLoader {
+    const uint4 *tile;
+    int64_t q0;
+    __device__ __forceinline__ Seg4 operator()(uint64_t s) const {
+        const uint32_t i = (uint32_t)((int64_t)s - q0);
+        const uint4 w = tile[i + (i >> 4)];
+        Seg4 r;
+        r.x = w.x; r.y = w.y; r.z = w.z; r.w = w.w;
+        return r;
+    }
+};
+
+template <bool EXACT, bool LONG>
+__global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const SyncParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint32_t s_exit[kSyncThreads];
     SyncLut L;
     sync_stage_tables(p.table, smem, L);
     __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 *tile = reinterpret_cast<uint4 *>(smem + sync_tables_bytes(p.table.lut_bits) + (size_t)warp * kSyncTileBytes);
+    const uint64_t n_units16 = (p.n_units + 3) >> 2;   // 16-byte units that hold stream data (last one may be partial)
 
-    const GlobalSegLoader ld{p.units, p.n_units};
-    const uint32_t tid = threadIdx.x;
-    const uint64_t chunk = (uint64_t)blockIdx.x * kSyncThreads + tid;
-    const bool active = chunk < p.n_chunks;
-    uint32_t entry = (chunk == 0) ? p.first_bit : 0u;
-    uint32_t word = 0;
-    bool merged;
-    if (active) word = sync_parse_chunk(ld, chunk, entry, L, false, 0u, merged);
-    s_exit[tid] = word >> 28;
     for (;;) {
-        __syncthreads();
-        const uint32_t xin = (tid == 0 || !active) ? entry : s_exit[tid - 1];
-        const bool redo = xin != entry;
-        __syncthreads();
-        if (redo) {
-            word = sync_parse_chunk(ld, chunk, xin, L, true, word, merged);
-            entry = xin;
-            s_exit[tid] = word >> 28;
+        uint32_t ticket = 0;
+        if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket >= p.n_tiles) break;
+        // ---- stage [halo | 512 segments | 1 look-ahead segment] of this warp tile ----
+        const int64_t q0 = (int64_t)ticket * kSyncTileSegs - kSyncHaloSegs;
+        __syncwarp();   // every lane is done reading the previous tile
+        for (uint32_t i = lane; i < kSyncTileUnits16; i += 32) {
+            const int64_t q = q0 + i;
+            uint32_t bytes = 0;
+            if (q >= 0 && (uint64_t)q < n_units16) {
+                const uint64_t rem = p.n_units - (uint64_t)q * 4;
+                bytes = rem >= 4 ? 16u : (uint32_t)rem * 4u;
+            }
+            // (a source address is needed even when nothing is copied)
+            cp_async16_zfill(tile + i + (i >> 4), p.units + (bytes ? (uint64_t)q * 4 : 0), bytes);
         }
-        if (!__syncthreads_or(redo ? 1 : 0)) break;
+        cp_async_commit_wait_all();
+        __syncwarp();
+
+        // ---- parse: 4 halo segments from bit 0, then the 16 segments of the chunk ----
+        const uint64_t chunk = (uint64_t)ticket * 32 + lane;
+        const bool active = chunk < p.n_chunks;
+        uint32_t words[2] = {0u, 0u};
+        uint32_t entry = 0;
+        if (active) {
+            uint32_t i = kSyncChunkSegs * lane;   // unit index (within the staged tile) of the halo start
+            uint32_t pos = 0;
+            if (chunk == 0) {
+                pos = p.first_bit;                // the stream's first chunk starts at a known offset: no halo
+                i += kSyncHaloSegs;
+            } else {
+#pragma unroll 1
+                for (uint32_t h = 0; h < kSyncHaloSegs; ++h, ++i) {
+                    const uint4 w = tile[i + (i >> 4)];
+                    const uint32_t n = tile[i + 1 + ((i + 1) >> 4)].x;
+                    pos = sync_segment<EXACT, LONG>(w.x, w.y, w.z, w.w, n, pos, L);
+                }
+            }
+            entry = pos;
+#pragma unroll 1
+            for (uint32_t g = 0; g < kSyncChunkSegs / 8; ++g) {
+                uint32_t word = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k, ++i) {
+                    const uint4 w = tile[i + (i >> 4)];
+                    const uint32_t n = tile[i + 1 + ((i + 1) >> 4)].x;
+                    pos = sync_segment<EXACT, LONG>(w.x, w.y, w.z, w.w, n, pos, L);
+                    word |= pos << (4u * k);
+                }
+                words[g] = word;
+            }
+        }
+        // ---- seams inside the warp tile: a lane whose halo parse had not merged yet (~20 % at the reference's
+        // redundancy 0.5) re-parses the head of its chunk from its left neighbour's landing, from the staged
+        // tile; repeated until no lane changes (a parse that fails to merge inside a chunk moves on one lane per
+        // round).  After this the tile is consistent given the entry of its FIRST chunk; K1b checks that one.
+        const TileSegLoader tld{tile, q0};
+        for (;;) {
+            const uint32_t left = __shfl_up_sync(0xffffffffu, words[1] >> 28, 1);
+            const bool redo = active && lane > 0 && left != entry;
+            if (!__any_sync(0xffffffffu, redo)) break;
+            if (redo) {
+                sync_repair_chunk<EXACT, LONG>(tld, chunk, left, L, words);
+                entry = left;
+            }
+        }
+        if (active) {
+            p.cur_entry[chunk] = (uint8_t)entry;
+            *reinterpret_cast<uint2 *>(p.gap_words + chunk * (kSyncChunkSegs / 8)) = make_uint2(words[0], words[1]);
+        }
     }
-    if (active) p.gap_words[chunk] = word;
-    if (tid == 0) p.blk_entry[blockIdx.x] = (uint8_t)entry;
 }
 
-// K1b: one thread per block seam.  Takes the (current) exit of the previous
-// block and re-parses the head of its own block until the parses merge.  If
-// the walk reaches the end of the block without merging, the block's exit has
-// changed and `changed` is bumped: the host launches another round (fixed
-// point; degrades to a sequential chain for codes that never synchronise).
-__global__ void __launch_bounds__(kSyncThreads) hd_sync_seams_kernel(const SyncParams p) {
+// K1b: seam check + repair.  One thread owns a GROUP of kSyncWalkChunks (= one
+// K1a warp tile) consecutive chunks and walks its seams in order: where the
+// landing of the previous chunk differs from the entry the chunk's landings
+// were parsed from, it re-parses the chunk head from the exact entry until the
+// parses merge (sync_repair_chunk), carrying the exact exit into the next chunk
+// (Gauss-Seidel inside the group; no two threads ever write the same chunk).
+// `changed` counts the groups whose EXIT changed: the host launches rounds until
+// it stays zero.  Two rounds suffice unless a parse fails to synchronise within a
+// whole group (64 Kbit); a code that never synchronises (all codewords the same
+// length not dividing 128) advances one group per round -- the true parse of
+// such a code is inherently sequential; this is the graceful worst case, the
+// reference emits garbage here.
+constexpr uint32_t kSyncWalkChunks = 32;
+
+template <bool EXACT, bool LONG>
+__global__ void __launch_bounds__(128) hd_sync_walk_kernel(const SyncParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     SyncLut L;
     sync_stage_tables(p.table, smem, L);
     __syncthreads();
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t c0 = g * kSyncWalkChunks;
+    if (c0 >= p.n_chunks) return;
+    uint64_t c1 = c0 + kSyncWalkChunks;
+    if (c1 > p.n_chunks) c1 = p.n_chunks;
+    const uint32_t kW = kSyncChunkSegs / 8;
     const GlobalSegLoader ld{p.units, p.n_units};
-    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;   // seam before block b
-    if (b >= p.n_blocks) return;
-    const uint64_t c0 = b * kSyncThreads;
-    const uint32_t xin = p.gap_words[c0 - 1] >> 28;
-    if (xin == p.blk_entry[b]) return;
-    uint64_t c_end = c0 + kSyncThreads;
-    if (c_end > p.n_chunks) c_end = p.n_chunks;
-    uint32_t entry = xin;
-    bool merged = false;
-    for (uint64_t c = c0; c < c_end; ++c) {
-        uint32_t word = p.gap_words[c];
-        word = sync_parse_chunk(ld, c, entry, L, true, word, merged);
-        p.gap_words[c] = word;
-        if (merged) break;
-        entry = word >> 28;
+    uint32_t xin = c0 == 0 ? p.first_bit : (p.gap_words[c0 * kW - 1] >> 28);
+    bool exit_changed = false;
+    for (uint64_t c = c0; c < c1; ++c) {
+        uint32_t words[2] = {p.gap_words[c * kW], p.gap_words[c * kW + 1]};
+        exit_changed = false;
+        if (xin != p.cur_entry[c]) {
+            const bool merged = sync_repair_chunk<EXACT, LONG>(ld, c, xin, L, words);
+            p.gap_words[c * kW] = words[0];
+            p.gap_words[c * kW + 1] = words[1];
+            p.cur_entry[c] = (uint8_t)xin;
+            exit_changed = !merged;
+        }
+        // K1a left every group consistent given the entry of its first chunk, and this walk keeps it so: once a
+        // chunk's exit is unchanged, nothing after it can change
+        if (!exit_changed) break;
+        xin = words[1] >> 28;
     }
-    p.blk_entry[b] = (uint8_t)xin;
-    if (!merged) atomicAdd(p.changed, 1u);
+    if (exit_changed) atomicAdd(p.changed, 1u);
 }
 
 }  // namespace hd

@@ -34,7 +34,7 @@ def lib():
                                       C.c_uint32]
         L.emul_sync.restype = C.c_int64
         L.emul_sync.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
-                                C.c_void_p, C.c_void_p]
+                                C.c_void_p, C.c_void_p, C.c_uint32]
         L.emul_table_info.restype = C.c_int
         L.emul_table_info.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         _lib = L
@@ -67,23 +67,24 @@ def decode_gap(units, gap_words, n_segments, n_symbols, flat_lut=None, pairs=Non
     return out[:got]
 
 
-def sync(units, flat_lut=None, pairs=None, first_bit=0):
+def sync(units, flat_lut=None, pairs=None, first_bit=0, exact=False):
+    """-> (gap words, rounds run, [chunks repaired in K1b round 1, K1c rounds])."""
     units = np.ascontiguousarray(units, dtype=np.uint32)
     f, fp, fb, p, pp, npairs = _tbl(flat_lut, pairs)
     n_seg = (len(units) + 3) // 4
-    n_chunks = (n_seg + 7) // 8
-    gw = np.zeros(max(n_chunks, 1), dtype=np.uint32)
+    n_chunks = (n_seg + 15) // 16
+    gw = np.zeros(max(2 * n_chunks, 1), dtype=np.uint32)
     rounds = np.zeros(4, dtype=np.uint32)
     r = lib().emul_sync(units.ctypes.data, len(units), first_bit, fp, fb, pp, npairs, gw.ctypes.data,
-                        rounds.ctypes.data)
+                        rounds.ctypes.data, 1 if exact else 0)
     if r < 0:
         raise RuntimeError("emul_sync failed: %d" % r)
-    return gw, int(r), int(rounds[0])
+    return gw, int(r), rounds[:2].tolist()
 
 
 def table_info(flat_lut=None, pairs=None):
     f, fp, fb, p, pp, npairs = _tbl(flat_lut, pairs)
     info = np.zeros(4, dtype=np.uint32)
     if lib().emul_table_info(fp, fb, pp, npairs, info.ctypes.data):
-        raise RuntimeError("bad table")
+        raise RuntimeError("emul_table_info failed")
     return dict(lut_bits=int(info[0]), min_len=int(info[1]), max_len=int(info[2]), has_long=int(info[3]))

@@ -14,6 +14,8 @@ using namespace hd;
 
 namespace {
 
+constexpr uint32_t kSyncWalkChunksEmul = 32;   // == kSyncWalkChunks of hd_kernels.cuh (device header)
+
 struct HostTables {
     TableBlob blob;
     DecodeTables T;
@@ -33,7 +35,6 @@ void bind(HostTables &h) {
     h.L.lm = h.blob.lut_bits;
     h.L.lt = h.T.lt;
     h.L.order = h.T.order;
-    h.L.has_long = h.blob.has_long != 0;
 }
 
 bool make_tables(const hd_lut_entry *flat, uint32_t flat_bits, const hd_sym_len *pairs, uint32_t n_pairs,
@@ -153,81 +154,114 @@ int64_t emul_decode_gap(const uint32_t *units, uint64_t n_units, const uint32_t 
     return -4;
 }
 
-// Re-enactment of hd_sync_chunks_kernel + hd_sync_seams_kernel rounds.
-// Returns the number of seam rounds run (>= 0) or negative on error.
-// rounds_out[0] = K1a intra-block iterations (max over blocks).
-int64_t emul_sync(const uint32_t *units, uint64_t n_units, uint32_t first_bit, const hd_lut_entry *flat,
-                  uint32_t flat_bits, const hd_sym_len *pairs, uint32_t n_pairs, uint32_t *gap_words_out,
-                  uint32_t *rounds_out) {
-    HostTables h;
-    if (!make_tables(flat, flat_bits, pairs, n_pairs, h)) return -1;
+}  // extern "C" (closed for the templates below)
+
+// Re-enactment of hd_sync_parse_kernel (K1a: halo + chunk per thread), the two
+// blind hd_sync_repair_kernel rounds (K1b, threads in ascending order) and, if
+// the second still changed a chunk exit, hd_sync_walk_kernel rounds (K1c).
+// Returns the number of repair/walk rounds run (>= 0) or negative on error.
+// rounds_out[0] = chunks repaired in K1b round 1, [1] = K1c rounds.
+template <bool EXACT, bool LONG>
+static int64_t emul_sync_t(HostTables &h, const uint32_t *units, uint64_t n_units, uint32_t first_bit,
+                           uint32_t *gap_words_out, uint32_t *rounds_out) {
     const uint64_t n_seg = (n_units + 3) / 4;
-    const uint64_t n_chunks = (n_seg + kChunkSegs - 1) / kChunkSegs;
-    const uint64_t n_blocks = (n_chunks + kSyncThreads - 1) / kSyncThreads;
+    const uint64_t n_chunks = (n_seg + kSyncChunkSegs - 1) / kSyncChunkSegs;
+    const uint32_t kW = kSyncChunkSegs / 8;
     HostSegLoader ld{units, n_units};
-    std::vector<uint8_t> blk_entry(n_blocks, 0);
-    uint32_t max_iters = 0;
-    // ---- K1a ----
-    for (uint64_t b = 0; b < n_blocks; ++b) {
-        uint32_t word[kSyncThreads] = {}, entry[kSyncThreads] = {}, s_exit[kSyncThreads] = {};
-        bool active[kSyncThreads];
-        bool merged;
-        for (uint32_t tid = 0; tid < kSyncThreads; ++tid) {
-            const uint64_t chunk = b * kSyncThreads + tid;
-            active[tid] = chunk < n_chunks;
-            entry[tid] = chunk == 0 ? first_bit : 0u;
-            if (active[tid]) word[tid] = sync_parse_chunk(ld, chunk, entry[tid], h.L, false, 0u, merged);
-            s_exit[tid] = word[tid] >> 28;
+    std::vector<uint8_t> cur_entry(n_chunks, 0);
+    // ---- K1a: speculative halo+chunk parse, then the in-warp-tile seam rounds ----
+    std::vector<uint32_t> ent(n_chunks, 0);
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+        uint64_t seg = c * kSyncChunkSegs;
+        uint32_t pos = 0;
+        if (c == 0) {
+            pos = first_bit;
+        } else {
+            for (uint64_t sg = seg - kSyncHaloSegs; sg < seg; ++sg) {
+                Seg4 w = ld(sg), n = ld(sg + 1);
+                pos = sync_segment<EXACT, LONG>(w.x, w.y, w.z, w.w, n.x, pos, h.L);
+            }
         }
-        uint32_t iters = 0;
+        ent[c] = pos;
+        for (uint32_t g = 0; g < kW; ++g) {
+            uint32_t word = 0;
+            for (uint32_t k = 0; k < 8; ++k, ++seg) {
+                Seg4 w = ld(seg), n = ld(seg + 1);
+                pos = sync_segment<EXACT, LONG>(w.x, w.y, w.z, w.w, n.x, pos, h.L);
+                if (pos > 15) return -3;
+                word |= pos << (4u * k);
+            }
+            gap_words_out[c * kW + g] = word;
+        }
+    }
+    for (uint64_t t0 = 0; t0 < n_chunks; t0 += 32) {   // one warp tile
+        const uint64_t t1 = t0 + 32 < n_chunks ? t0 + 32 : n_chunks;
         for (;;) {
-            ++iters;
-            uint32_t xin[kSyncThreads];
+            uint32_t left[32];
             bool any = false;
-            for (uint32_t tid = 0; tid < kSyncThreads; ++tid)
-                xin[tid] = (tid == 0 || !active[tid]) ? entry[tid] : s_exit[tid - 1];
-            for (uint32_t tid = 0; tid < kSyncThreads; ++tid) {
-                if (xin[tid] == entry[tid]) continue;
+            for (uint64_t c = t0 + 1; c < t1; ++c) left[c - t0] = gap_words_out[(c - 1) * kW + kW - 1] >> 28;   // shuffle
+            for (uint64_t c = t0 + 1; c < t1; ++c) {
+                if (left[c - t0] == ent[c]) continue;
                 any = true;
-                const uint64_t chunk = b * kSyncThreads + tid;
-                word[tid] = sync_parse_chunk(ld, chunk, xin[tid], h.L, true, word[tid], merged);
-                entry[tid] = xin[tid];
-                s_exit[tid] = word[tid] >> 28;
+                uint32_t words[2] = {gap_words_out[c * kW], gap_words_out[c * kW + 1]};
+                sync_repair_chunk<EXACT, LONG>(ld, c, left[c - t0], h.L, words);
+                gap_words_out[c * kW] = words[0];
+                gap_words_out[c * kW + 1] = words[1];
+                ent[c] = left[c - t0];
             }
             if (!any) break;
         }
-        if (iters > max_iters) max_iters = iters;
-        for (uint32_t tid = 0; tid < kSyncThreads; ++tid)
-            if (active[tid]) gap_words_out[b * kSyncThreads + tid] = word[tid];
-        blk_entry[b] = (uint8_t)entry[0];
     }
-    if (rounds_out) rounds_out[0] = max_iters;
-    // ---- K1b rounds until no block exit changes ----
+    for (uint64_t c = 0; c < n_chunks; ++c) cur_entry[c] = (uint8_t)ent[c];
+    // ---- K1b rounds: two blind ones, then until no group exit changes ----
+    if (rounds_out) { rounds_out[0] = 0; rounds_out[1] = 0; }
     int64_t rounds = 0;
-    for (;; ++rounds) {
-        uint32_t changed = 0;
-        for (uint64_t b = 1; b < n_blocks; ++b) {
-            const uint64_t c0 = b * kSyncThreads;
-            const uint32_t xin = gap_words_out[c0 - 1] >> 28;
-            if (xin == blk_entry[b]) continue;
-            uint64_t c_end = c0 + kSyncThreads;
-            if (c_end > n_chunks) c_end = n_chunks;
-            uint32_t entry = xin;
-            bool merged = false;
-            for (uint64_t c = c0; c < c_end; ++c) {
-                uint32_t w = sync_parse_chunk(ld, c, entry, h.L, true, gap_words_out[c], merged);
-                gap_words_out[c] = w;
-                if (merged) break;
-                entry = w >> 28;
+    const uint64_t n_groups = (n_chunks + kSyncWalkChunksEmul - 1) / kSyncWalkChunksEmul;
+    for (uint64_t r = 0; r <= n_groups + 2; ++r) {
+        uint32_t ch = 0;
+        std::vector<uint8_t> exit_before(n_chunks);
+        for (uint64_t c = 0; c < n_chunks; ++c) exit_before[c] = (uint8_t)(gap_words_out[c * kW + kW - 1] >> 28);
+        for (uint64_t g = 0; g < n_groups; ++g) {
+            const uint64_t c0 = g * kSyncWalkChunksEmul;
+            uint64_t c1 = c0 + kSyncWalkChunksEmul;
+            if (c1 > n_chunks) c1 = n_chunks;
+            uint32_t xin = c0 == 0 ? first_bit : exit_before[c0 - 1];
+            bool exit_changed = false;
+            for (uint64_t c = c0; c < c1; ++c) {
+                uint32_t words[2] = {gap_words_out[c * kW], gap_words_out[c * kW + 1]};
+                exit_changed = false;
+                if (xin != cur_entry[c]) {
+                    const bool merged = sync_repair_chunk<EXACT, LONG>(ld, c, xin, h.L, words);
+                    gap_words_out[c * kW] = words[0];
+                    gap_words_out[c * kW + 1] = words[1];
+                    cur_entry[c] = (uint8_t)xin;
+                    exit_changed = !merged;
+                }
+                if (!exit_changed) break;
+                xin = words[1] >> 28;
             }
-            blk_entry[b] = (uint8_t)xin;
-            if (!merged) ++changed;
+            if (exit_changed) ++ch;
         }
-        if (!changed) break;
-        if ((uint64_t)rounds > n_blocks + 2) return -2;
+        ++rounds;
+        if (rounds_out) rounds_out[1] += 1;
+        if (!ch && rounds >= 2) return rounds;
     }
-    return rounds + 1;
+    return -2;
 }
+
+extern "C" int64_t emul_sync(const uint32_t *units, uint64_t n_units, uint32_t first_bit, const hd_lut_entry *flat,
+                             uint32_t flat_bits, const hd_sym_len *pairs, uint32_t n_pairs, uint32_t *gap_words_out,
+                             uint32_t *rounds_out, uint32_t exact) {
+    HostTables h;
+    if (!make_tables(flat, flat_bits, pairs, n_pairs, h)) return -1;
+    const bool lng = h.blob.has_long != 0;
+    if (exact) return lng ? emul_sync_t<true, true>(h, units, n_units, first_bit, gap_words_out, rounds_out)
+                          : emul_sync_t<true, false>(h, units, n_units, first_bit, gap_words_out, rounds_out);
+    return lng ? emul_sync_t<false, true>(h, units, n_units, first_bit, gap_words_out, rounds_out)
+               : emul_sync_t<false, false>(h, units, n_units, first_bit, gap_words_out, rounds_out);
+}
+
+extern "C" {
 
 // table introspection for tests
 int emul_table_info(const hd_lut_entry *flat, uint32_t flat_bits, const hd_sym_len *pairs, uint32_t n_pairs,

@@ -352,11 +352,21 @@ def test_selfsync_shards_with_halo(hd, torch_cuda, world):
     assert hd.seams_ok(infos) == []
     assert sum(c for _, c in placed) == n
     assert np.array_equal(whole, data)
-    # entry offsets equal the oracle's true parse
+    # every entry offset is a codeword boundary of the oracle's true parse at or after the first one of its segment
+    # (the fast synchronisation records where a whole LUT jump lands, see sync_segment in csrc/hd_core.h)
     off, cnt = O.sync_points(units, lut, n)
     plan = hd.plan_shards(len(units), world)
+    codes, lens = O.canonical_codes(pairs[:, 0], pairs[:, 1])
     for g in range(1, world):
-        assert int(infos[g][1]) == int(off[plan[g][0]])
+        seg = plan[g][0]
+        assert int(off[seg]) <= int(infos[g][1]) <= 15
+        # walk the true parse from the segment's first codeword: the entry must be one of its boundaries
+        k = int(cnt[:seg].sum())
+        pos = int(off[seg])
+        while pos < int(infos[g][1]):
+            pos += int(lens[data[k]])
+            k += 1
+        assert pos == int(infos[g][1])
 
 
 def test_selfsync_shards_repair_when_code_never_synchronises(hd, torch_cuda):
