@@ -83,7 +83,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
     def start(self):
         if self.nv:
@@ -300,7 +300,6 @@ def ours(args):
         step()
         ev[i][1].record(stream)
     barrier()
-    clk = clocks.stop()
     launches = hd.launch_count() - launches0
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
     if dist is not None:
@@ -320,6 +319,7 @@ def ours(args):
             kern[k] += v / args.steps
     hd.profile_enable(False)
     barrier()
+    clk = clocks.stop()   # sampled over the timed region and the per-kernel pass of the same workload
     if world == 1:
         n_units_local, n_sym_local = len(units), n_total
     else:
@@ -402,7 +402,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mib", type=int, default=100, help="original MiB per GPU (demo.cc: MB = 2^20 B)")
     ap.add_argument("--redundancy", type=float, default=0.5)
-    ap.add_argument("--cpu-sample-mib", type=int, default=4)
+    ap.add_argument("--cpu-sample-mib", type=int, default=32)
     ap.add_argument("--ref-sample-mib", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

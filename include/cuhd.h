@@ -1,0 +1,270 @@
+/*
+ * cuhd.h -- source-compatible C++ surface of the reference's CUHD library
+ * (gpuhd/include/cuhd.h:11-21 and the headers it pulls in), re-declared fresh
+ * over the C ABI of hd_b200.h so that the reference demos compile against the
+ * B200 decoder unchanged.  Header-only; needs the CUDA runtime and
+ * libhd_b200.so.  Same names, argument meaning and error behaviour (CUDA
+ * errors print and exit(1) like CUERR, gpuhd/include/cuhd_cuda_definitions.h:
+ * 21-28); the work is done by hd_decode_selfsync.
+ */
+#ifndef CUHD_SHIM_H_
+#define CUHD_SHIM_H_
+
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <string>
+#include <utility>
+
+#include "hd_b200.h"
+
+/* gpuhd/include/cuhd_constants.h:15-24 */
+#ifndef MAX_CODEWORD_LENGTH
+#define MAX_CODEWORD_LENGTH 11
+#endif
+#ifndef UNIT_TYPE
+#define UNIT_TYPE std::uint32_t
+#endif
+#ifndef SYMBOL_TYPE
+#define SYMBOL_TYPE std::uint8_t
+#endif
+#ifndef BIT_COUNT_TYPE
+#define BIT_COUNT_TYPE std::uint8_t
+#endif
+
+/* gpuhd/include/cuhd_cuda_definitions.h:21-28 */
+#ifndef CUERR
+#define CUERR                                                                            \
+    {                                                                                    \
+        cudaError_t cuhd_err__ = cudaGetLastError();                                     \
+        if (cuhd_err__ != cudaSuccess) {                                                 \
+            std::printf("CUDA error: %s : %s, line %d\n", cudaGetErrorString(cuhd_err__), \
+                        __FILE__, __LINE__);                                             \
+            std::exit(1);                                                                \
+        }                                                                                \
+    }
+#endif
+/* gpuhd/include/cuhd_util.h:29-42 */
+#ifndef TIMER_START
+#define TIMER_START(vec, label) vec.push_back(cuhd::CUHDUtil::time(label, [&]() {
+#define TIMER_STOP }));
+#endif
+#ifndef SDIV
+#define SDIV(n, m) (((n) + (m)-1) / (m))
+#endif
+
+namespace cuhd {
+
+inline void cuhd_check(cudaError_t e, const char *file, int line) {
+    if (e != cudaSuccess) {
+        std::printf("CUDA error: %s : %s, line %d\n", cudaGetErrorString(e), file, line);
+        std::exit(1);
+    }
+}
+inline void cuhd_check_hd(hd_status s, const char *what) {
+    if (s != HD_OK) {
+        std::printf("CUDA error: %s failed: %s (%s)\n", what, hd_status_string(s), hd_last_cuda_error());
+        std::exit(1);
+    }
+}
+#define CUHD_CHECK(call) ::cuhd::cuhd_check((call), __FILE__, __LINE__)
+
+/* gpuhd/include/cuhd_codetable.h:20-44 */
+struct CUHDCodetableItemSingle {
+    BIT_COUNT_TYPE num_bits;
+    SYMBOL_TYPE symbol;
+};
+static_assert(sizeof(CUHDCodetableItemSingle) == sizeof(hd_lut_entry), "LUT entry layout");
+
+class CUHDCodetable {
+   public:
+    explicit CUHDCodetable(size_t num_entries)
+        : size_(num_entries), max_codeword_length_(0), table_(new CUHDCodetableItemSingle[num_entries]()) {
+        size_t n = num_entries;
+        while (n > 1) { n >>= 1; ++max_codeword_length_; }
+    }
+    size_t get_size() { return size_; }
+    size_t get_num_entries() { return size_; }
+    size_t get_max_codeword_length() { return max_codeword_length_; }
+    CUHDCodetableItemSingle *get() { return table_.get(); }
+
+   private:
+    size_t size_, max_codeword_length_;
+    std::unique_ptr<CUHDCodetableItemSingle[]> table_;
+};
+
+/* gpuhd/include/cuhd_subsequence_sync_point.h:17-22 (layout kept for source compatibility; the B200 decoder keeps 4
+ * bits per subsequence in its workspace instead of 16 bytes) */
+struct CUHDSubsequenceSyncPoint {
+    std::uint32_t last_word_unit;
+    std::uint32_t last_word_bit;
+    std::uint32_t num_symbols;
+    std::uint32_t sequence_synced;
+};
+
+/* gpuhd/include/cuhd_input_buffer.h:22-29, gpuhd/src/cuhd_input_buffer.cc:13-32: copies the stream and appends one
+ * zero unit */
+class CUHDInputBuffer {
+   public:
+    CUHDInputBuffer(std::uint8_t *buffer, size_t size)
+        : compressed_size_units_(SDIV(size, sizeof(UNIT_TYPE)) + 1), compressed_size_(size) {
+        // 16-byte aligned: the decoder loads 128-bit subsequences
+        void *p = nullptr;
+        if (posix_memalign(&p, 64, compressed_size_units_ * sizeof(UNIT_TYPE))) std::exit(1);
+        buffer_.reset(static_cast<UNIT_TYPE *>(p));
+        std::memset(buffer_.get(), 0, compressed_size_units_ * sizeof(UNIT_TYPE));
+        std::memcpy(buffer_.get(), buffer, size);
+    }
+    UNIT_TYPE *get_compressed_data() { return buffer_.get(); }
+    size_t get_compressed_size() { return compressed_size_; }
+    size_t get_compressed_size_units() { return compressed_size_units_; }
+    size_t get_unit_size() { return sizeof(UNIT_TYPE); }
+
+   private:
+    struct FreeDeleter { void operator()(UNIT_TYPE *p) const { std::free(p); } };
+    size_t compressed_size_units_, compressed_size_;
+    std::unique_ptr<UNIT_TYPE[], FreeDeleter> buffer_;
+};
+
+/* gpuhd/include/cuhd_output_buffer.h:22-28 */
+class CUHDOutputBuffer {
+   public:
+    explicit CUHDOutputBuffer(size_t size) : uncompressed_size_(size), buffer_(new SYMBOL_TYPE[size]()) {}
+    std::unique_ptr<SYMBOL_TYPE[]> &get_decompressed_data() { return buffer_; }
+    size_t get_uncompressed_size() { return uncompressed_size_; }
+    size_t get_symbol_size() { return sizeof(SYMBOL_TYPE); }
+
+   private:
+    size_t uncompressed_size_;
+    std::unique_ptr<SYMBOL_TYPE[]> buffer_;
+};
+
+/* gpuhd/include/cuhd_gpu_memory_buffer.h:23-30, .hxx:18-67: non-owning host pointer + owning device pointer */
+template <typename T>
+class CUHDGPUMemoryBuffer {
+   public:
+    CUHDGPUMemoryBuffer(T *buffer, size_t size) : buffer_host_(buffer), buffer_device_(nullptr), size_(size) {}
+    virtual ~CUHDGPUMemoryBuffer() { free(); }
+    T *get() { return buffer_device_; }
+    virtual void allocate() {
+        if (!buffer_device_) CUHD_CHECK(cudaMalloc(reinterpret_cast<void **>(&buffer_device_), size_ * sizeof(T) + 16));
+    }
+    virtual void free() {
+        if (buffer_device_) { cudaFree(buffer_device_); buffer_device_ = nullptr; }
+    }
+    virtual void cpy_host_to_device() {
+        CUHD_CHECK(cudaMemcpy(buffer_device_, buffer_host_, size_ * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    virtual void cpy_device_to_host() {
+        CUHD_CHECK(cudaMemcpy(buffer_host_, buffer_device_, size_ * sizeof(T), cudaMemcpyDeviceToHost));
+    }
+
+   protected:
+    T *buffer_host_;
+    T *buffer_device_;
+    size_t size_;
+};
+
+class CUHDGPUInputBuffer : public CUHDGPUMemoryBuffer<UNIT_TYPE> {
+   public:
+    explicit CUHDGPUInputBuffer(std::shared_ptr<CUHDInputBuffer> b)
+        : CUHDGPUMemoryBuffer<UNIT_TYPE>(b->get_compressed_data(), b->get_compressed_size_units()), input_buffer_(b) {}
+
+   private:
+    std::shared_ptr<CUHDInputBuffer> input_buffer_;
+};
+
+class CUHDGPUOutputBuffer : public CUHDGPUMemoryBuffer<SYMBOL_TYPE> {
+   public:
+    explicit CUHDGPUOutputBuffer(std::shared_ptr<CUHDOutputBuffer> b)
+        : CUHDGPUMemoryBuffer<SYMBOL_TYPE>(b->get_decompressed_data().get(), b->get_uncompressed_size()), output_buffer_(b) {}
+
+   private:
+    std::shared_ptr<CUHDOutputBuffer> output_buffer_;
+};
+
+/* gpuhd/include/cuhd_gpu_codetable.h: device mirror of the flat LUT.  cpy_host_to_device() additionally builds the
+ * decoder's own device tables (multi-symbol LUT, sync LUT) from it. */
+class CUHDGPUCodetable : public CUHDGPUMemoryBuffer<CUHDCodetableItemSingle> {
+   public:
+    explicit CUHDGPUCodetable(std::shared_ptr<CUHDCodetable> t)
+        : CUHDGPUMemoryBuffer<CUHDCodetableItemSingle>(t->get(), t->get_size()), table_(t), handle_(nullptr) {}
+    ~CUHDGPUCodetable() override { hd_table_free(handle_); }
+    void cpy_host_to_device() override {
+        CUHDGPUMemoryBuffer<CUHDCodetableItemSingle>::cpy_host_to_device();
+        hd_table_free(handle_);
+        handle_ = nullptr;
+        cuhd_check_hd(hd_table_from_flat_lut(reinterpret_cast<const hd_lut_entry *>(table_->get()),
+                                             (uint32_t)table_->get_max_codeword_length(), nullptr, &handle_),
+                      "hd_table_from_flat_lut");
+        CUHD_CHECK(cudaStreamSynchronize(nullptr));
+    }
+    const hd_table *handle() const { return handle_; }
+
+   private:
+    std::shared_ptr<CUHDCodetable> table_;
+    hd_table *handle_;
+};
+
+/* gpuhd/include/cuhd_gpu_decoder_memory.h:22-33: caller-allocated auxiliary memory of the decoder */
+class CUHDGPUDecoderMemory {
+   public:
+    CUHDGPUDecoderMemory(size_t num_units, size_t /*subsequence_size*/, size_t /*num_threads*/)
+        : num_units_(num_units), bytes_(hd_workspace_bytes_selfsync(num_units)), ws_(nullptr) {}
+    ~CUHDGPUDecoderMemory() { free(); }
+    void allocate() {
+        if (!ws_) CUHD_CHECK(cudaMalloc(&ws_, bytes_));
+    }
+    void free() {
+        if (ws_) { cudaFree(ws_); ws_ = nullptr; }
+    }
+    void retrieve_sync_data() {}   // the B200 decoder keeps no per-subsequence sync structs to copy back
+    CUHDSubsequenceSyncPoint *get_sync_info() { return nullptr; }
+    std::uint32_t *get_output_sizes() { return nullptr; }
+    std::uint8_t *get_sequence_synced_device() { return nullptr; }
+    std::uint8_t *get_sequence_synced_host() { return nullptr; }
+    void *workspace() { return ws_; }
+    size_t workspace_bytes() const { return bytes_; }
+
+   private:
+    size_t num_units_, bytes_;
+    void *ws_;
+};
+
+/* gpuhd/include/cuhd_gpu_decoder.h:24-32 == gpuhd/src/cuhd_gpu_decoder.cu:422-523 */
+class CUHDGPUDecoder {
+   public:
+    static void decode(std::shared_ptr<CUHDGPUInputBuffer> input, size_t input_size,
+                       std::shared_ptr<CUHDGPUOutputBuffer> output, size_t output_size,
+                       std::shared_ptr<CUHDGPUCodetable> table, std::shared_ptr<CUHDGPUDecoderMemory> aux,
+                       size_t /*max_codeword_length*/, size_t /*preferred_subsequence_size*/,
+                       size_t /*threads_per_block*/) {
+        // subsequence size and block shape are the decoder's own business on B200 (128-bit subsequences,
+        // persistent CTAs); the arguments are accepted for source compatibility
+        cuhd_check_hd(hd_decode_selfsync(input->get(), input_size, table->handle(), output->get(), output_size,
+                                         aux->workspace(), aux->workspace_bytes(), nullptr),
+                      "hd_decode_selfsync");
+    }
+};
+
+/* gpuhd/include/cuhd_util.h:25-42, gpuhd/src/cuhd_util.cc:13-55 */
+class CUHDUtil {
+   public:
+    static std::pair<std::string, size_t> time(std::string s, std::function<void()> f) {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        f();
+        auto t1 = std::chrono::high_resolution_clock::now();
+        return std::make_pair(s, (size_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count());
+    }
+    static bool equals(SYMBOL_TYPE *a, SYMBOL_TYPE *b, size_t size) { return std::memcmp(a, b, size) == 0; }
+    static size_t optimal_subsequence_size(size_t, size_t, size_t pref, size_t) { return pref; }
+};
+
+}  // namespace cuhd
+#endif /* CUHD_SHIM_H_ */

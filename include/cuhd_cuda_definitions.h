@@ -1,0 +1,2 @@
+/* cuhd_cuda_definitions.h -- include-path compatibility with gpuhd/include/cuhd_cuda_definitions.h: everything lives in cuhd.h */
+#include "cuhd.h"

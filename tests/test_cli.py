@@ -1,0 +1,75 @@
+"""The CLI binaries with the reference's argv shapes: bin/encoder (host), bin/decoder, bin/demo,
+bin/multigpu_demo.  The encoder is checked on CPU against the oracle's .huff reader; the decoders run on the GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import _oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "cse375-finalproj-huffman-decoding_b200", "bin")
+
+
+def _need(name):
+    path = os.path.join(BIN, name)
+    if not os.path.exists(path):
+        pytest.skip("%s not built (make -C cse375-finalproj-huffman-decoding_b200)" % name)
+    return path
+
+
+def test_encoder_cli_writes_a_huff_the_oracle_decodes(tmp_path):
+    enc = _need("encoder")
+    data = O.generate(300_001, 0.5, seed=5)
+    src = tmp_path / "in.bin"
+    data.tofile(src)
+    out = subprocess.run([enc, str(src), str(tmp_path / "a.huff")], capture_output=True, text=True, check=True).stdout
+    assert "Original size: 300001 bytes" in out
+    image = np.fromfile(tmp_path / "a.huff", dtype=np.uint8)
+    assert np.array_equal(O.huff_decode(image, len(data)), data)
+    assert subprocess.run([enc], capture_output=True).returncode != 0      # usage + failure without arguments
+
+
+@pytest.mark.gpu
+def test_decoder_cli_roundtrip(tmp_path):
+    enc, dec = _need("encoder"), _need("decoder")
+    for r, n in ((0.5, 2_000_003), (0.0, 100_000), (1.0, 777_777)):
+        data = O.generate(n, r, seed=int(r * 10) + 1)
+        data.tofile(tmp_path / "in.bin")
+        subprocess.run([enc, str(tmp_path / "in.bin"), str(tmp_path / "a.huff")], check=True, capture_output=True)
+        out = subprocess.run([dec, str(tmp_path / "a.huff"), str(tmp_path / "out.bin")], capture_output=True, text=True,
+                             check=True).stdout
+        assert "Original size: %d bytes" % n in out and "HtoD," in out and "Throughput:" in out
+        assert np.array_equal(np.fromfile(tmp_path / "out.bin", dtype=np.uint8), data)
+
+
+@pytest.mark.gpu
+def test_demo_cli_shapes(tmp_path):
+    demo, mg = _need("demo"), _need("multigpu_demo")
+    work = tmp_path / "run"
+    work.mkdir()
+    out = subprocess.run([demo, "0", "8"], cwd=work, capture_output=True, text=True, check=True).stdout
+    assert "Compression time.. " in out and "Decompression throughput (mb/s): " in out and "mismatch" not in out
+    assert (tmp_path / "data100_100.bin").stat().st_size == 8 << 20          # saved like the reference does
+    out2 = subprocess.run([demo, "0", "8"], cwd=work, capture_output=True, text=True, check=True).stdout
+    assert "Input source: Read 8 MB from file" in out2 and "mismatch" not in out2
+    assert subprocess.run([demo, "-1", "8"], cwd=work, capture_output=True).returncode == 1
+    out3 = subprocess.run([mg, "1", "16"], cwd=work, capture_output=True, text=True, check=True).stdout
+    assert "Multi-GPU Parallel Decode Time (Full Span).. " in out3 and "mismatch" not in out3
+    assert subprocess.run([mg, "99", "16"], cwd=work, capture_output=True).returncode == 1
+
+
+@pytest.mark.gpu
+def test_reference_demo_source_runs_on_our_library(tmp_path):
+    """oracle/_ref/gpuhd_demo_b200 = the reference's gpuhd/src/demo.cc, unmodified, compiled against include/cuhd.h +
+    include/llhuff.h and linked with libhd_b200.so (oracle/Makefile): the drop-in claim of INTEGRATION.md section 1."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "gpuhd_demo_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gpuhd_demo_b200 not built (needs /root/reference at build time)")
+    work = tmp_path / "run"
+    work.mkdir()
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "cse375-finalproj-huffman-decoding_b200") + ":" +
+               os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([exe, "0", "16"], cwd=work, capture_output=True, text=True, check=True, env=env).stdout
+    assert "Decompression throughput (mb/s):" in out and "mismatch" not in out
