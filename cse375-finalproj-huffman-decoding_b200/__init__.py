@@ -48,7 +48,8 @@ ABI_SYMBOLS = [
     "hd_huff_decode_host", "hd_build_code", "hd_flat_lut_from_lengths", "hd_encoded_size", "hd_encode",
     "hd_huff_write", "hd_generate", "hd_shard_segments", "hd_host_decoder_create", "hd_host_decoder_destroy",
     "hd_host_decode_selfsync", "hd_host_decode_huff", "hd_selfsync_decode_host", "hd_profile_enable",
-    "hd_profile_read", "hd_launch_count", "hd_decode_selfsync_shard", "hd_set_tuning", "hd_set_trace",
+    "hd_profile_read", "hd_launch_count", "hd_decode_selfsync_shard", "hd_set_tuning", "hd_set_trace", "hd_decode_selfsync_enqueue",
+    "hd_decode_selfsync_finish",
 ]
 PROFILE_SLOTS = ("sync_chunks", "sync_seams", "decode_write", "reserved")
 
@@ -84,6 +85,8 @@ def lib():
     L.hd_decode_selfsync.argtypes = [vp, u64, vp, vp, u64, vp, sz, vp]
     L.hd_decode_selfsync_ex.argtypes = [vp, u64, u32, vp, vp, u64, vp, sz, vp, vp]
     L.hd_selfsync_gap_array.argtypes = [vp, u64, u32, vp, vp, vp, sz, vp]
+    L.hd_decode_selfsync_enqueue.argtypes = [vp, u64, u32, vp, vp, u64, vp, sz, vp, vp, vp]
+    L.hd_decode_selfsync_finish.argtypes = [vp, u64, u32, vp, vp, u64, vp, sz, vp, vp, vp]
     L.hd_huff_parse.argtypes = [vp, sz, C.POINTER(_HuffView)]
     L.hd_huff_image_bytes.argtypes = [u64, u32, u32]
     L.hd_huff_image_bytes.restype = sz
@@ -290,15 +293,30 @@ class Decoder:
         self.ws_bytes = nbytes
         self.count = torch.zeros(1, dtype=torch.int64, device="cuda")
 
-    def decode_selfsync(self, d_units, table, n_symbols, out=None, first_bit=0):
-        """cuhd::CUHDGPUDecoder::decode (gpuhd/src/cuhd_gpu_decoder.cu:422-523)."""
+    def decode_selfsync(self, d_units, table, n_symbols, out=None, first_bit=0, defer=False):
+        """cuhd::CUHDGPUDecoder::decode (gpuhd/src/cuhd_gpu_decoder.cu:422-523).  defer=True only enqueues the work
+        (hd_decode_selfsync_enqueue); call finish() before using the output."""
         torch = _torch()
         if out is None:
             out = torch.empty(n_symbols, dtype=torch.uint8, device="cuda")
-        _check(lib().hd_decode_selfsync_ex(d_units.data_ptr(), d_units.numel(), first_bit, table.handle,
-                                           out.data_ptr(), n_symbols, self.ws_ptr, self.ws_bytes,
-                                           self.count.data_ptr(), _stream_ptr(torch)), "hd_decode_selfsync")
+        if not defer:
+            _check(lib().hd_decode_selfsync_ex(d_units.data_ptr(), d_units.numel(), first_bit, table.handle,
+                                               out.data_ptr(), n_symbols, self.ws_ptr, self.ws_bytes,
+                                               self.count.data_ptr(), _stream_ptr(torch)), "hd_decode_selfsync")
+            return out
+        if getattr(self, "_flag", None) is None:
+            self._flag = torch.zeros(16, dtype=torch.int32).pin_memory()
+        self._pending = (d_units.data_ptr(), d_units.numel(), first_bit, table.handle, out.data_ptr(), n_symbols,
+                         self.ws_ptr, self.ws_bytes, self.count.data_ptr(), self._flag.data_ptr(), _stream_ptr(torch))
+        self._keep = (d_units, table, out)
+        _check(lib().hd_decode_selfsync_enqueue(*self._pending), "hd_decode_selfsync_enqueue")
         return out
+
+    def finish(self):
+        """Second half of a deferred decode_selfsync: synchronise, check convergence, repair if needed."""
+        if getattr(self, "_pending", None) is not None:
+            _check(lib().hd_decode_selfsync_finish(*self._pending), "hd_decode_selfsync_finish")
+            self._pending = None
 
     def decode_gap(self, d_units, d_gap_words, table, n_symbols, out=None, first_bit=0, n_segments=None):
         """decoder_l1_l2 / gpu_dec_l1_l2 (Huffman_coding_Gap_arrays/decoder/src/decoder.cu:454-815)."""

