@@ -279,7 +279,7 @@ SyncLaunch make_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_b
     p.n_units = n_units_readable > n_units ? n_units_readable : n_units;
     p.n_segments = div_up(n_units, kSegmentUnits);
     p.n_chunks = div_up(p.n_segments, kSyncChunkSegs);
-    p.n_tiles = div_up(p.n_chunks, 32);
+    p.n_tiles = std::max<uint64_t>(1, div_up(p.n_chunks - 1, kSyncTileChunks));   // tile t owns chunks 31t+1 .. 31t+31 (+ chunk 0)
     p.first_bit = first_bit;
     p.table = table_dev(table);
     p.gap_words = d_gap_words;
@@ -311,9 +311,10 @@ hd_status launch_sync_walk(const SyncLaunch &L, uint32_t *changed, cudaStream_t 
     SyncParams p = L.p;
     p.changed = changed;
     auto kern = hd_sync_walk_kernel<EXACT, LONG>;
-    HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_tables));
-    const unsigned grid = (unsigned)div_up(div_up(p.n_chunks, kSyncWalkChunks), 128);
-    kern<<<grid, 128, L.smem_tables, s>>>(p);
+    const size_t smem = L.smem_tables + 128 * (kSyncChunkSegs + 2) * 16;   // + one chunk slot per thread
+    HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, div_up(div_up(p.n_chunks - 1, kSyncWalkChunks), 128));
+    kern<<<grid, 128, smem, s>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     HD_CUDA(cudaGetLastError());
     return HD_OK;
@@ -352,7 +353,7 @@ hd_status finish_sync(const SyncLaunch &L, cudaStream_t s, bool *extra_rounds) {
     if (h_changed == 0) return HD_OK;
     *extra_rounds = true;
     uint32_t *changed = L.p.changed + 2;
-    const uint64_t max_rounds = div_up(L.p.n_chunks, kSyncWalkChunks) + 2;
+    const uint64_t max_rounds = div_up(L.p.n_chunks, kSyncWalkChunks) + 3;
     for (uint64_t round = 0; round <= max_rounds; ++round) {
         HD_CUDA(cudaMemsetAsync(changed, 0, 4, s));
         hd_status st = HD_SYNC_DISPATCH(launch_sync_walk, L, changed, s);

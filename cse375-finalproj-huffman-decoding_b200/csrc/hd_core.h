@@ -212,22 +212,34 @@ struct Seg4 {
 //     (encoder.cu:307-312), needed by hd_selfsync_gap_array.
 // Merge test of the reference: cuhd_gpu_decoder.cu:208-213.
 template <bool EXACT, bool LONG>
+HD_HD uint32_t sync_step(uint32_t win, uint32_t pos, const SyncLut &L) {
+    uint32_t ent = L.lut[win >> L.idx_shift];
+    if (LONG) {
+        if (ent == 0) {
+            const uint32_t first = (resolve_long(win, L.lm, L.lt, L.order) >> 16) & 0xffu;
+            ent = first | (first << 8);
+        }
+    }
+    uint32_t step = ent & 0xffu;
+    if (EXACT) {
+        if (pos + step > kSegmentBits) step = ent >> 8;
+    }
+    return step;
+}
+
+template <bool EXACT, bool LONG>
 HD_HD uint32_t sync_segment(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4, uint32_t pos,
                             const SyncLut &L) {
+    // Two table steps per window slide: a step is at most 16 bits, so the 32-bit window taken at `pos` still holds
+    // the 16 bits the second step looks at (hi << step1), and the pair crosses at most one unit boundary.  The second
+    // step is dropped when the first already left the segment, so the sequence of positions -- and therefore every
+    // landing -- is exactly that of single steps.
     while (pos < kSegmentBits) {
         const uint32_t win = funnel_l(r1, r0, pos);
-        uint32_t ent = L.lut[win >> L.idx_shift];
-        if (LONG) {
-            if (ent == 0) {
-                const uint32_t first = (resolve_long(win, L.lm, L.lt, L.order) >> 16) & 0xffu;
-                ent = first | (first << 8);
-            }
-        }
-        uint32_t step = ent & 0xffu;
-        if (EXACT) {
-            if (pos + step > kSegmentBits) step = ent >> 8;
-        }
-        const uint32_t np = pos + step;
+        const uint32_t s1 = sync_step<EXACT, LONG>(win, pos, L);
+        const uint32_t p1 = pos + s1;
+        const uint32_t s2 = sync_step<EXACT, LONG>(win << s1, p1, L);
+        const uint32_t np = p1 < kSegmentBits ? p1 + s2 : p1;
         if ((np ^ pos) & 32u) {
             r0 = r1; r1 = r2; r2 = r3; r3 = r4;
 #if defined(__CUDA_ARCH__)

@@ -22,7 +22,11 @@ constexpr uint32_t kMaxCodeLen = 16;     // .huff MAX_CODEWORD_LENGTH (decoder/i
 constexpr uint32_t kSyncChunkSegs = 16;  // segments per sync thread (2048 bits = two gap words)
 constexpr uint32_t kSyncHaloSegs = 4;    // segments parsed speculatively BEFORE the chunk (512 bits)
 constexpr uint32_t kSyncWarps = 24;      // warps per persistent sync CTA (one CTA per SM)
-constexpr uint32_t kSyncTileSegs = 32 * kSyncChunkSegs;                   // segments per warp tile
+// A warp tile stages 32 chunks but OWNS only 31: lane 0 re-parses the last chunk of the previous tile (whose owner
+// is lane 31 there) just to hand lane 1 an exit offset that had a whole chunk to synchronise -- so the seams between
+// warp tiles are right without any communication between warps (3 % redundant parsing).
+constexpr uint32_t kSyncTileChunks = 31;                                  // chunks owned per warp tile
+constexpr uint32_t kSyncTileSegs = 32 * kSyncChunkSegs;                   // segments staged per warp tile
 constexpr uint32_t kSyncTileUnits16 = kSyncHaloSegs + kSyncTileSegs + 1;  // 16-byte units staged per warp tile
 constexpr uint32_t kSyncTileBytes = (kSyncTileUnits16 + kSyncTileUnits16 / 16 + 2) * 16;   // + 1 pad unit per 16
 

@@ -586,7 +586,8 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket >= p.n_tiles) break;
         // ---- stage [halo | 512 segments | 1 look-ahead segment] of this warp tile ----
-        const int64_t q0 = (int64_t)ticket * kSyncTileSegs - kSyncHaloSegs;
+        const uint64_t chunk0 = (uint64_t)ticket * kSyncTileChunks;   // lane 0's chunk (owned by the previous tile)
+        const int64_t q0 = (int64_t)(chunk0 * kSyncChunkSegs) - kSyncHaloSegs;
         __syncwarp();   // every lane is done reading the previous tile
         for (uint32_t i = lane; i < kSyncTileUnits16; i += 32) {
             const int64_t q = q0 + i;
@@ -602,8 +603,9 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
         __syncwarp();
 
         // ---- parse: 4 halo segments from bit 0, then the 16 segments of the chunk ----
-        const uint64_t chunk = (uint64_t)ticket * 32 + lane;
+        const uint64_t chunk = chunk0 + lane;
         const bool active = chunk < p.n_chunks;
+        const bool owner = active && (lane > 0 || ticket == 0);
         uint32_t words[2] = {0u, 0u};
         uint32_t entry = 0;
         if (active) {
@@ -648,12 +650,19 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
                 entry = left;
             }
         }
-        if (active) {
+        if (owner) {
             p.cur_entry[chunk] = (uint8_t)entry;
             *reinterpret_cast<uint2 *>(p.gap_words + chunk * (kSyncChunkSegs / 8)) = make_uint2(words[0], words[1]);
         }
     }
 }
+
+// loads segment s from a thread-private shared-memory copy of one chunk that starts at segment seg0
+struct SlotSegLoader {
+    const Seg4 *slot;
+    uint64_t seg0;
+    __device__ __forceinline__ Seg4 operator()(uint64_t s) const { return slot[s - seg0]; }
+};
 
 // K1b: seam check + repair.  One thread owns a GROUP of kSyncWalkChunks (= one
 // K1a warp tile) consecutive chunks and walks its seams in order: where the
@@ -667,7 +676,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
 // length not dividing 128) advances one group per round -- the true parse of
 // such a code is inherently sequential; this is the graceful worst case, the
 // reference emits garbage here.
-constexpr uint32_t kSyncWalkChunks = 32;
+constexpr uint32_t kSyncWalkChunks = kSyncTileChunks;   // group g = the chunks owned by K1a tile g: [31g+1, 31g+32)
 
 template <bool EXACT, bool LONG>
 __global__ void __launch_bounds__(128) hd_sync_walk_kernel(const SyncParams p) {
@@ -676,19 +685,26 @@ __global__ void __launch_bounds__(128) hd_sync_walk_kernel(const SyncParams p) {
     sync_stage_tables(p.table, smem, L);
     __syncthreads();
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t c0 = g * kSyncWalkChunks;
+    const uint64_t c0 = g * kSyncWalkChunks + 1;   // chunk 0 starts at a known offset and is never repaired
     if (c0 >= p.n_chunks) return;
     uint64_t c1 = c0 + kSyncWalkChunks;
     if (c1 > p.n_chunks) c1 = p.n_chunks;
     const uint32_t kW = kSyncChunkSegs / 8;
     const GlobalSegLoader ld{p.units, p.n_units};
-    uint32_t xin = c0 == 0 ? p.first_bit : (p.gap_words[c0 * kW - 1] >> 28);
+    // a repair first pulls the whole chunk (+2 look-ahead segments) into this thread's shared-memory slot with
+    // back-to-back 128-bit loads, so that the parse pays ONE global-memory latency instead of one per segment
+    Seg4 *slot = reinterpret_cast<Seg4 *>(smem + sync_tables_bytes(p.table.lut_bits)) + (size_t)threadIdx.x * (kSyncChunkSegs + 2);
+    uint32_t xin = p.gap_words[c0 * kW - 1] >> 28;
     bool exit_changed = false;
     for (uint64_t c = c0; c < c1; ++c) {
         uint32_t words[2] = {p.gap_words[c * kW], p.gap_words[c * kW + 1]};
         exit_changed = false;
         if (xin != p.cur_entry[c]) {
-            const bool merged = sync_repair_chunk<EXACT, LONG>(ld, c, xin, L, words);
+            const uint64_t seg0 = c * kSyncChunkSegs;
+#pragma unroll
+            for (uint32_t k = 0; k < kSyncChunkSegs + 2; ++k) slot[k] = ld(seg0 + k);
+            const SlotSegLoader sld{slot, seg0};
+            const bool merged = sync_repair_chunk<EXACT, LONG>(sld, c, xin, L, words);
             p.gap_words[c * kW] = words[0];
             p.gap_words[c * kW + 1] = words[1];
             p.cur_entry[c] = (uint8_t)xin;

@@ -14,7 +14,7 @@ using namespace hd;
 
 namespace {
 
-constexpr uint32_t kSyncWalkChunksEmul = 32;   // == kSyncWalkChunks of hd_kernels.cuh (device header)
+constexpr uint32_t kSyncWalkChunksEmul = hd::kSyncTileChunks;   // == kSyncWalkChunks of hd_kernels.cuh (device header)
 
 struct HostTables {
     TableBlob blob;
@@ -194,24 +194,40 @@ static int64_t emul_sync_t(HostTables &h, const uint32_t *units, uint64_t n_unit
             gap_words_out[c * kW + g] = word;
         }
     }
-    for (uint64_t t0 = 0; t0 < n_chunks; t0 += 32) {   // one warp tile
+    // one warp tile = chunks [31t, 31t+32); lane 0 (chunk 31t, t > 0) is owned by the previous tile: its parse runs
+    // here on private copies (from its own halo) only to give lane 1 an exit offset
+    std::vector<uint32_t> fin_words(gap_words_out, gap_words_out + n_chunks * kW);   // spec results of every chunk
+    std::vector<uint32_t> fin_ent(ent);
+    const uint64_t n_tiles_k1 = n_chunks > 1 ? (n_chunks - 1 + kSyncTileChunks - 1) / kSyncTileChunks : 1;
+    for (uint64_t t = 0; t < n_tiles_k1; ++t) {
+        const uint64_t t0 = t * kSyncTileChunks;
         const uint64_t t1 = t0 + 32 < n_chunks ? t0 + 32 : n_chunks;
+        uint32_t w[32][2], e[32];
+        for (uint64_t c = t0; c < t1; ++c) {   // every lane starts from its speculative (halo) parse
+            w[c - t0][0] = gap_words_out[c * kW];
+            w[c - t0][1] = gap_words_out[c * kW + 1];
+            e[c - t0] = ent[c];
+        }
         for (;;) {
             uint32_t left[32];
             bool any = false;
-            for (uint64_t c = t0 + 1; c < t1; ++c) left[c - t0] = gap_words_out[(c - 1) * kW + kW - 1] >> 28;   // shuffle
-            for (uint64_t c = t0 + 1; c < t1; ++c) {
-                if (left[c - t0] == ent[c]) continue;
+            for (uint64_t l = 1; l < t1 - t0; ++l) left[l] = w[l - 1][1] >> 28;   // shuffle
+            for (uint64_t l = 1; l < t1 - t0; ++l) {
+                if (left[l] == e[l]) continue;
                 any = true;
-                uint32_t words[2] = {gap_words_out[c * kW], gap_words_out[c * kW + 1]};
-                sync_repair_chunk<EXACT, LONG>(ld, c, left[c - t0], h.L, words);
-                gap_words_out[c * kW] = words[0];
-                gap_words_out[c * kW + 1] = words[1];
-                ent[c] = left[c - t0];
+                sync_repair_chunk<EXACT, LONG>(ld, t0 + l, left[l], h.L, w[l]);
+                e[l] = left[l];
             }
             if (!any) break;
         }
+        for (uint64_t l = (t == 0 ? 0 : 1); l < t1 - t0; ++l) {   // owners write
+            fin_words[(t0 + l) * kW] = w[l][0];
+            fin_words[(t0 + l) * kW + 1] = w[l][1];
+            fin_ent[t0 + l] = e[l];
+        }
     }
+    for (uint64_t i = 0; i < n_chunks * kW; ++i) gap_words_out[i] = fin_words[i];
+    ent = fin_ent;
     for (uint64_t c = 0; c < n_chunks; ++c) cur_entry[c] = (uint8_t)ent[c];
     // ---- K1b rounds: two blind ones, then until no group exit changes ----
     if (rounds_out) { rounds_out[0] = 0; rounds_out[1] = 0; }
@@ -222,10 +238,11 @@ static int64_t emul_sync_t(HostTables &h, const uint32_t *units, uint64_t n_unit
         std::vector<uint8_t> exit_before(n_chunks);
         for (uint64_t c = 0; c < n_chunks; ++c) exit_before[c] = (uint8_t)(gap_words_out[c * kW + kW - 1] >> 28);
         for (uint64_t g = 0; g < n_groups; ++g) {
-            const uint64_t c0 = g * kSyncWalkChunksEmul;
+            const uint64_t c0 = g * kSyncWalkChunksEmul + 1;
+            if (c0 >= n_chunks) continue;
             uint64_t c1 = c0 + kSyncWalkChunksEmul;
             if (c1 > n_chunks) c1 = n_chunks;
-            uint32_t xin = c0 == 0 ? first_bit : exit_before[c0 - 1];
+            uint32_t xin = exit_before[c0 - 1];
             bool exit_changed = false;
             for (uint64_t c = c0; c < c1; ++c) {
                 uint32_t words[2] = {gap_words_out[c * kW], gap_words_out[c * kW + 1]};
