@@ -264,10 +264,8 @@ def ours(args):
     else:
         from hd_b200 import ShardedSelfSyncDecoder
         shard = ShardedSelfSyncDecoder(units, table, n_total, rank, world, dist=dist)
-        step = shard.step
-
-        def finish():
-            pass
+        step = shard.step      # enqueue the shard decode + the NCCL all-gather, no host synchronisation
+        finish = shard.wait    # stream sync + convergence flag (collective only if some rank had to decode again)
 
     flush = torch.zeros(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()

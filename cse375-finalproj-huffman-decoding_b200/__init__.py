@@ -49,7 +49,7 @@ ABI_SYMBOLS = [
     "hd_huff_write", "hd_generate", "hd_shard_segments", "hd_host_decoder_create", "hd_host_decoder_destroy",
     "hd_host_decode_selfsync", "hd_host_decode_huff", "hd_selfsync_decode_host", "hd_profile_enable",
     "hd_profile_read", "hd_launch_count", "hd_decode_selfsync_shard", "hd_set_tuning", "hd_set_trace", "hd_decode_selfsync_enqueue",
-    "hd_decode_selfsync_finish",
+    "hd_decode_selfsync_finish", "hd_decode_selfsync_shard_enqueue", "hd_decode_selfsync_shard_finish",
 ]
 PROFILE_SLOTS = ("sync_chunks", "sync_seams", "decode_write", "reserved")
 
@@ -114,6 +114,8 @@ def lib():
     L.hd_set_trace.argtypes = [vp]
     L.hd_set_trace.restype = None
     L.hd_decode_selfsync_shard.argtypes = [vp, u64, u64, u64, u32, vp, vp, u64, vp, sz, vp, vp]
+    L.hd_decode_selfsync_shard_enqueue.argtypes = [vp, u64, u64, u64, u32, vp, vp, u64, vp, sz, vp, vp, vp]
+    L.hd_decode_selfsync_shard_finish.argtypes = [vp, u64, u64, u64, u32, vp, vp, u64, vp, sz, vp, vp, vp]
     _lib = L
     return L
 

@@ -553,10 +553,9 @@ hd_status hd_decode_selfsync_ex(const uint32_t *d_units, uint64_t n_units, uint3
 // when it enters the shard; the entry offset it reaches and the offset at which
 // the shard's parse leaves are reported so that neighbours can be checked
 // against each other (entry of rank g == exit of rank g-1).
-hd_status hd_decode_selfsync_shard(const uint32_t *d_units, uint64_t n_units_halo, uint64_t n_units_shard,
-                                   uint64_t n_units_readable, uint32_t first_bit, const hd_table *table,
-                                   uint8_t *d_out, uint64_t out_cap, void *d_workspace, size_t workspace_bytes,
-                                   uint64_t *d_shard_info, void *stream) {
+static hd_status shard_args(const uint32_t *d_units, uint64_t n_units_halo, uint64_t n_units_shard,
+                            uint64_t &n_units_readable, uint32_t first_bit, const hd_table *table, uint8_t *d_out,
+                            uint64_t out_cap, void *d_workspace, size_t workspace_bytes) {
     const uint64_t n_units = n_units_halo + n_units_shard;
     hd_status st = check_common(d_units, n_units, table, d_out, out_cap, d_workspace);
     if (st != HD_OK) return st;
@@ -564,21 +563,84 @@ hd_status hd_decode_selfsync_shard(const uint32_t *d_units, uint64_t n_units_hal
     if (n_units_halo % (kSegmentUnits * 8)) return HD_ERR_INVALID;   // gap words (8 segments each) must line up
     if (n_units_readable < n_units) n_units_readable = n_units;
     if (workspace_bytes < ws_bytes(n_units, true)) return HD_ERR_WORKSPACE;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    Workspace w = carve(d_workspace, n_units, true);
-    HD_CUDA(cudaMemsetAsync(w.changed, 0, kCtrlBytes, s));
-    const SyncLaunch L = make_sync(d_units, n_units, n_units_halo ? 0u : first_bit, table, w.gap_words, w.blk_entry,
-                                   w.changed, n_units_readable, false);
-    st = run_sync(L, s);
-    if (st != HD_OK) return st;
-    bool extra = false;
-    st = finish_sync(L, s, &extra);
-    if (st != HD_OK) return st;
+    return HD_OK;
+}
+
+static hd_status shard_decode(const uint32_t *d_units, uint64_t n_units_halo, uint64_t n_units_shard,
+                              uint64_t n_units_readable, uint32_t first_bit, const hd_table *table, uint8_t *d_out,
+                              uint64_t out_cap, const Workspace &w, uint64_t *d_shard_info, cudaStream_t s,
+                              bool already_zeroed) {
     const uint64_t halo_words = n_units_halo / (kSegmentUnits * 8);
     const uint32_t *gaps = w.gap_words + halo_words;
     return run_gap_decode(d_units + n_units_halo, n_units_shard, gaps, div_up(n_units_shard, kSegmentUnits), first_bit,
                           table, d_out, out_cap, w, nullptr, s, n_units_readable - n_units_halo,
-                          n_units_halo ? gaps - 1 : nullptr, d_shard_info);
+                          n_units_halo ? gaps - 1 : nullptr, d_shard_info, already_zeroed);
+}
+
+// asynchronous half (see hd_decode_selfsync_enqueue)
+hd_status hd_decode_selfsync_shard_enqueue(const uint32_t *d_units, uint64_t n_units_halo, uint64_t n_units_shard,
+                                           uint64_t n_units_readable, uint32_t first_bit, const hd_table *table,
+                                           uint8_t *d_out, uint64_t out_cap, void *d_workspace,
+                                           size_t workspace_bytes, uint64_t *d_shard_info, uint32_t *h_unconverged,
+                                           void *stream) {
+    hd_status st = shard_args(d_units, n_units_halo, n_units_shard, n_units_readable, first_bit, table, d_out, out_cap,
+                              d_workspace, workspace_bytes);
+    if (st != HD_OK) return st;
+    if (!h_unconverged) return HD_ERR_INVALID;
+    *h_unconverged = 0;
+    const uint64_t n_units = n_units_halo + n_units_shard;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Workspace w = carve(d_workspace, n_units, true);
+    HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes + kCtrlBytes, s));
+    const SyncLaunch L = make_sync(d_units, n_units, n_units_halo ? 0u : first_bit, table, w.gap_words, w.blk_entry,
+                                   w.changed, n_units_readable, false);
+    st = run_sync(L, s);
+    if (st != HD_OK) return st;
+    st = shard_decode(d_units, n_units_halo, n_units_shard, n_units_readable, first_bit, table, d_out, out_cap, w,
+                      d_shard_info, s, true);
+    if (st != HD_OK) return st;
+    if (L.p.n_chunks > 1) HD_CUDA(cudaMemcpyAsync(h_unconverged, w.changed + 1, 4, cudaMemcpyDeviceToHost, s));
+    return HD_OK;
+}
+
+// synchronous half (see hd_decode_selfsync_finish)
+hd_status hd_decode_selfsync_shard_finish(const uint32_t *d_units, uint64_t n_units_halo, uint64_t n_units_shard,
+                                          uint64_t n_units_readable, uint32_t first_bit, const hd_table *table,
+                                          uint8_t *d_out, uint64_t out_cap, void *d_workspace,
+                                          size_t workspace_bytes, uint64_t *d_shard_info,
+                                          const uint32_t *h_unconverged, void *stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    HD_CUDA(cudaStreamSynchronize(s));
+    if (!h_unconverged || *h_unconverged == 0) return HD_OK;
+    hd_status st = shard_args(d_units, n_units_halo, n_units_shard, n_units_readable, first_bit, table, d_out, out_cap,
+                              d_workspace, workspace_bytes);
+    if (st != HD_OK) return st;
+    const uint64_t n_units = n_units_halo + n_units_shard;
+    Workspace w = carve(d_workspace, n_units, true);
+    const SyncLaunch L = make_sync(d_units, n_units, n_units_halo ? 0u : first_bit, table, w.gap_words, w.blk_entry,
+                                   w.changed, n_units_readable, false);
+    bool extra = false;
+    st = finish_sync(L, s, &extra);
+    if (st != HD_OK) return st;
+    st = shard_decode(d_units, n_units_halo, n_units_shard, n_units_readable, first_bit, table, d_out, out_cap, w,
+                      d_shard_info, s, false);
+    if (st != HD_OK) return st;
+    HD_CUDA(cudaStreamSynchronize(s));
+    return HD_OK;
+}
+
+hd_status hd_decode_selfsync_shard(const uint32_t *d_units, uint64_t n_units_halo, uint64_t n_units_shard,
+                                   uint64_t n_units_readable, uint32_t first_bit, const hd_table *table,
+                                   uint8_t *d_out, uint64_t out_cap, void *d_workspace, size_t workspace_bytes,
+                                   uint64_t *d_shard_info, void *stream) {
+    static thread_local uint32_t *h_flag = nullptr;   // pinned, one per host thread
+    if (!h_flag) HD_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&h_flag), 64, cudaHostAllocDefault));
+    hd_status st = hd_decode_selfsync_shard_enqueue(d_units, n_units_halo, n_units_shard, n_units_readable, first_bit,
+                                                    table, d_out, out_cap, d_workspace, workspace_bytes, d_shard_info,
+                                                    h_flag, stream);
+    if (st != HD_OK) return st;
+    return hd_decode_selfsync_shard_finish(d_units, n_units_halo, n_units_shard, n_units_readable, first_bit, table,
+                                           d_out, out_cap, d_workspace, workspace_bytes, d_shard_info, h_flag, stream);
 }
 
 hd_status hd_decode_selfsync(const uint32_t *d_units, uint64_t n_units, const hd_table *table, uint8_t *d_out,

@@ -104,21 +104,48 @@ class ShardedSelfSyncDecoder:
         self.all_info = torch.zeros(world * 3, dtype=torch.int64, device="cuda")
         self.count_local = 0
         self.offset = 0
+        self._flag = None
+        self._pending = None
 
-    def _decode(self, first_bit=0, halo=True):
+    def _args(self, first_bit, halo):
         hu = self.n_units_halo if halo else 0
         ptr = self.d_units.data_ptr() + 4 * (self.n_units_halo - hu)
-        self._check(self._lib.hd_decode_selfsync_shard(
-            C.c_void_p(ptr), hu, self.n_units_local, self.n_units_readable - (self.n_units_halo - hu), first_bit,
-            self.table.handle, C.c_void_p(self.out.data_ptr()), self.out_cap, C.c_void_p(self.ws_ptr), self.ws_bytes,
-            C.c_void_p(self.info.data_ptr()), self._stream_ptr(self.torch)), "hd_decode_selfsync_shard")
+        return (C.c_void_p(ptr), hu, self.n_units_local, self.n_units_readable - (self.n_units_halo - hu), first_bit,
+                self.table.handle, C.c_void_p(self.out.data_ptr()), self.out_cap, C.c_void_p(self.ws_ptr), self.ws_bytes,
+                C.c_void_p(self.info.data_ptr()))
+
+    def _decode(self, first_bit=0, halo=True):
+        """Synchronous shard decode (hd_decode_selfsync_shard)."""
+        self._check(self._lib.hd_decode_selfsync_shard(*self._args(first_bit, halo), self._stream_ptr(self.torch)),
+                    "hd_decode_selfsync_shard")
 
     def step(self):
-        """The timed step: local shard decode + the all-gather of {count, entry, exit} (async on the stream)."""
-        self._decode()
+        """The timed step, entirely on the stream: local shard decode (hd_decode_selfsync_shard_enqueue) + the
+        all-gather of {count, entry, exit}.  Call wait() before using the results."""
+        if self._flag is None:
+            self._flag = self.torch.zeros(16, dtype=self.torch.int32).pin_memory()
+        self._pending = self._args(0, True) + (C.c_void_p(self._flag.data_ptr()), self._stream_ptr(self.torch))
+        self._check(self._lib.hd_decode_selfsync_shard_enqueue(*self._pending), "hd_decode_selfsync_shard_enqueue")
         if self.dist is not None and self.world > 1:
             self.dist.all_gather_into_tensor(self.all_info, self.info)
         else:
+            self.all_info.copy_(self.info)
+
+    def wait(self):
+        """Host half of a step: synchronise; in the rare unconverged case finish the synchronisation, decode again
+        and re-gather (hd_decode_selfsync_shard_finish)."""
+        if self._pending is None:
+            return
+        self._check(self._lib.hd_decode_selfsync_shard_finish(*self._pending), "hd_decode_selfsync_shard_finish")
+        redone = int(self._flag[0].item())
+        self._pending = None
+        # every rank must take part in a re-gather if ANY rank had to decode again
+        if self.dist is not None and self.world > 1:
+            t = self.torch.tensor([redone], dtype=self.torch.int64, device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            if int(t.item()):
+                self.dist.all_gather_into_tensor(self.all_info, self.info)
+        elif redone:
             self.all_info.copy_(self.info)
 
     def _gather(self):
@@ -130,6 +157,7 @@ class ShardedSelfSyncDecoder:
 
     def finish(self):
         """Host side of the exchange: check the seams, repair if a halo was too short, place the outputs."""
+        self.wait()
         infos = self.all_info.cpu().numpy().reshape(self.world, 3)
         placed = resolve_seams(self.rank, self.world, infos, self._gather,
                                lambda first_bit: self._decode(first_bit=first_bit, halo=False), self.n_symbols)
@@ -158,6 +186,7 @@ class ShardedSelfSyncDecoder:
             t0 = time.perf_counter()
             self.d_units.copy_(h_in, non_blocking=True)
             self.step()
+            self.wait()
             h_out.copy_(self.out[:self.count_local], non_blocking=True)
             torch.cuda.synchronize()
             if i:

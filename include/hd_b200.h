@@ -169,6 +169,27 @@ hd_status hd_decode_selfsync_shard(const uint32_t *d_units, uint64_t n_units_hal
                                    size_t workspace_bytes,
                                    uint64_t *d_shard_info, void *stream);
 
+/* the same split in two, like hd_decode_selfsync_enqueue / _finish: _enqueue
+ * only queues work on `stream` (so that the caller can queue its NCCL
+ * all-gather of d_shard_info right behind it), _finish synchronises and
+ * handles the rare unconverged case. */
+hd_status hd_decode_selfsync_shard_enqueue(const uint32_t *d_units, uint64_t n_units_halo,
+                                           uint64_t n_units_shard,
+                                           uint64_t n_units_readable,
+                                           uint32_t first_bit, const hd_table *table,
+                                           uint8_t *d_out, uint64_t out_cap,
+                                           void *d_workspace, size_t workspace_bytes,
+                                           uint64_t *d_shard_info,
+                                           uint32_t *h_unconverged, void *stream);
+hd_status hd_decode_selfsync_shard_finish(const uint32_t *d_units, uint64_t n_units_halo,
+                                          uint64_t n_units_shard,
+                                          uint64_t n_units_readable,
+                                          uint32_t first_bit, const hd_table *table,
+                                          uint8_t *d_out, uint64_t out_cap,
+                                          void *d_workspace, size_t workspace_bytes,
+                                          uint64_t *d_shard_info,
+                                          const uint32_t *h_unconverged, void *stream);
+
 /* Synchronisation only (phases 1-2 of the reference, cuhd_gpu_decoder.cu:
  * 145-327): writes the gap array of the stream -- for every 128-bit
  * subsequence k>0 the bit offset of the first codeword starting in it, packed
