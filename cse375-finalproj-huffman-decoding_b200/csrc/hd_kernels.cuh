@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             }
             // wait for the scan warp's prefix of tile k-1 (computed while we decoded tile k): a flag, not a
             // barrier, so that with two output tiles no decode warp ever waits for another decode warp
-            while (ld_acquire_cta_u32(&s_ready[b ^ 1u]) < k) __nanosleep(64);
+            while (ld_acquire_cta_u32(&s_ready[b ^ 1u]) < k) __nanosleep(200);
         }
         if (valid) prefetch(s_tileid[(k + 1u) % 3u]);   // from the prologue or published with s_ready above
         if (prev_valid) {

@@ -445,3 +445,12 @@ def test_selfsync_enqueue_finish_split(hd, torch_cuda):
             assert np.array_equal(out.cpu().numpy(), data)
             assert int(dec.count.item()) == n
         tab.close()
+
+
+@pytest.mark.parametrize("r", [0.0, 0.9, 1.0])
+def test_1GiB_redundancy_sweep_roundtrip(hd, torch_cuda, r):
+    """configs[4]: redundancy sweep at 1 GB (near-incompressible ... highly skewed; r=0.5 is covered above).
+    Self-sync scheme with the llhuff 11-bit limit, byte-exact against the original."""
+    n = 1 << 30
+    same, cnt = _roundtrip_large(hd, torch_cuda, n, r, "selfsync")
+    assert same and cnt == n
