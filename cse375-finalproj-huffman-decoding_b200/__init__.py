@@ -49,7 +49,8 @@ ABI_SYMBOLS = [
     "hd_huff_write", "hd_generate", "hd_shard_segments", "hd_host_decoder_create", "hd_host_decoder_destroy",
     "hd_host_decode_selfsync", "hd_host_decode_huff", "hd_selfsync_decode_host", "hd_profile_enable",
     "hd_profile_read", "hd_launch_count", "hd_decode_selfsync_shard", "hd_set_tuning", "hd_set_trace", "hd_decode_selfsync_enqueue",
-    "hd_decode_selfsync_finish", "hd_decode_selfsync_shard_enqueue", "hd_decode_selfsync_shard_finish",
+    "hd_decode_selfsync_finish", "hd_table_from_lengths_device", "hd_table_blob",
+    "hd_decode_selfsync_shard_enqueue", "hd_decode_selfsync_shard_finish",
 ]
 PROFILE_SLOTS = ("sync_chunks", "sync_seams", "decode_write", "reserved")
 
@@ -71,6 +72,8 @@ def lib():
     L.hd_table_from_flat_lut.argtypes = [vp, u32, vp, C.POINTER(vp)]
     L.hd_table_from_lengths.argtypes = [vp, u32, vp, C.POINTER(vp)]
     L.hd_table_free.argtypes = [vp]
+    L.hd_table_from_lengths_device.argtypes = [vp, u32, vp, C.POINTER(vp)]
+    L.hd_table_blob.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.hd_table_free.restype = None
     L.hd_table_max_length.argtypes = [vp]
     L.hd_table_max_length.restype = u32
@@ -240,10 +243,13 @@ def _stream_ptr(torch):
 class Codetable:
     """Device decode tables; mirrors cuhd::CUHDGPUCodetable (gpuhd/include/cuhd_gpu_codetable.h)."""
 
-    def __init__(self, flat_lut=None, pairs=None):
+    def __init__(self, flat_lut=None, pairs=None, device_pairs=None):
         torch = _torch()
         h = C.c_void_p(None)
-        if flat_lut is not None:
+        if device_pairs is not None:     # uint8 CUDA tensor [n, 2] {symbol, length}: tables are built by a kernel
+            _check(lib().hd_table_from_lengths_device(device_pairs.data_ptr(), device_pairs.shape[0],
+                                                      _stream_ptr(torch), C.byref(h)), "hd_table_from_lengths_device")
+        elif flat_lut is not None:
             f = np.ascontiguousarray(flat_lut, dtype=np.uint8)
             bits = int(f.shape[0]).bit_length() - 1
             _check(lib().hd_table_from_flat_lut(f.ctypes.data, bits, _stream_ptr(torch), C.byref(h)),
@@ -254,6 +260,14 @@ class Codetable:
                    "hd_table_from_lengths")
         torch.cuda.current_stream().synchronize()   # the host blob may go away after this
         self.handle = h
+
+    def blob(self):
+        """The device table blob as a numpy byte array (for tests)."""
+        size = C.c_size_t(0)
+        _check(lib().hd_table_blob(self.handle, None, 0, C.byref(size)), "hd_table_blob")
+        out = np.zeros(size.value, dtype=np.uint8)
+        _check(lib().hd_table_blob(self.handle, out.ctypes.data, size.value, C.byref(size)), "hd_table_blob")
+        return out
 
     @property
     def max_length(self):

@@ -12,6 +12,7 @@
 #include <new>
 
 #include "hd_kernels.cuh"
+#include "hd_tables.cuh"
 
 using namespace hd;
 
@@ -418,6 +419,58 @@ hd_status hd_table_from_lengths(const hd_sym_len *pairs, uint32_t n_pairs, void 
     HostCode c;
     if (!code_from_pairs(pairs, n_pairs, c)) return HD_ERR_FORMAT;
     return upload_table(c, stream, out);
+}
+
+// K0: the whole blob is built by a kernel from a DEVICE-resident {symbol,length} list; only a 16-byte summary comes
+// back (the host needs lut_bits / min_len / max_len to pick kernel variants and shared-memory geometry).
+hd_status hd_table_from_lengths_device(const hd_sym_len *d_pairs, uint32_t n_pairs, void *stream, hd_table **out) {
+    if (!out || !d_pairs || n_pairs == 0 || n_pairs > 256) return HD_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    hd_table *t = new (std::nothrow) hd_table();
+    if (!t) return HD_ERR_INVALID;
+    TableSummary *d_sum = nullptr;
+    TableSummary h_sum = {0, 0, 0, 0};
+    cudaError_t e = cudaGetDevice(&t->device);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&t->d_blob), kTableBlobMaxBytes);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&d_sum), sizeof(TableSummary));
+    if (e == cudaSuccess) e = cudaMemsetAsync(t->d_blob, 0, kTableBlobMaxBytes, s);
+    if (e == cudaSuccess) {
+        hd_build_tables_kernel<<<1, 1024, 0, s>>>(d_pairs, n_pairs, t->d_blob, d_sum);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_sum, d_sum, sizeof(h_sum), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (d_sum) cudaFree(d_sum);
+    if (e != cudaSuccess || !h_sum.ok) {
+        if (e != cudaSuccess) { g_last_cuda = e; (void)cudaGetLastError(); }
+        if (t->d_blob) cudaFree(t->d_blob);
+        delete t;
+        return e != cudaSuccess ? HD_ERR_CUDA : HD_ERR_FORMAT;
+    }
+    TableBlob &b = t->host;
+    const uint32_t n = 1u << h_sum.lut_bits;
+    b.lut_bits = h_sum.lut_bits;
+    b.min_len = h_sum.min_len;
+    b.max_len = h_sum.max_len;
+    b.has_long = h_sum.max_len > h_sum.lut_bits ? 1u : 0u;
+    b.off_sync = n * 4;
+    b.off_len = b.off_sync + n * 2;
+    b.off_order = b.off_len + 256;
+    b.off_long = b.off_order + 256;
+    b.total_bytes = (uint32_t)align_up(b.off_long + sizeof(LongTables), 16);
+    *out = t;
+    return HD_OK;
+}
+
+// device copy of a table's blob (tests compare the device-built blob with the host-built one)
+hd_status hd_table_blob(const hd_table *t, void *dst, size_t cap, size_t *size) {
+    if (!t || !t->d_blob) return HD_ERR_INVALID;
+    if (size) *size = t->host.total_bytes;
+    if (!dst) return HD_OK;
+    if (cap < t->host.total_bytes) return HD_ERR_INVALID;
+    HD_CUDA(cudaMemcpy(dst, t->d_blob, t->host.total_bytes, cudaMemcpyDeviceToHost));
+    return HD_OK;
 }
 
 void hd_table_free(hd_table *t) {

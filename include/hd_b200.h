@@ -74,6 +74,16 @@ hd_status hd_table_from_flat_lut(const hd_lut_entry *lut, uint32_t lut_bits,
  * Lengths 1..16. */
 hd_status hd_table_from_lengths(const hd_sym_len *pairs, uint32_t n_pairs,
                                 void *stream, hd_table **out);
+/* Same tables built ON THE DEVICE by a kernel from a device-resident list
+ * (e.g. the header of a .huff image that is already in HBM): no host-side
+ * table construction and no table upload; only a 16-byte summary is read back.
+ * Replaces get_table_info/get_twolevel_table (decoder/src/get_table.cpp:3-139)
+ * and get_decoder_table (llhuffman_encoder.cc:240-262).  Synchronises `stream`. */
+hd_status hd_table_from_lengths_device(const hd_sym_len *d_pairs, uint32_t n_pairs,
+                                       void *stream, hd_table **out);
+/* copies the table's device blob to host memory (dst may be NULL to query the
+ * size); for tests and debugging */
+hd_status hd_table_blob(const hd_table *t, void *dst, size_t cap, size_t *size);
 void hd_table_free(hd_table *t);
 uint32_t hd_table_max_length(const hd_table *t);
 uint32_t hd_table_min_length(const hd_table *t);

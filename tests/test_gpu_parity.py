@@ -454,3 +454,38 @@ def test_1GiB_redundancy_sweep_roundtrip(hd, torch_cuda, r):
     n = 1 << 30
     same, cnt = _roundtrip_large(hd, torch_cuda, n, r, "selfsync")
     assert same and cnt == n
+
+
+def test_device_built_tables_equal_host_built(hd, torch_cuda):
+    """the table kernel (hd_table_from_lengths_device) writes, byte for byte, the blob that the host
+    builder uploads -- for generate.cpp codes of every redundancy, fixed-length codes, 16-bit codes, one symbol."""
+    torch = torch_cuda
+    lists = []
+    for r in cases.SWEEP:
+        data = O.generate(200_000, r, seed=int(r * 100) + 9)
+        lists.append(hd.build_code(data, 16))
+        lists.append(hd.build_code(data, 11))
+    lists += [cases.fixed_length_code(8, 3), cases.fixed_length_code(256, 8), cases.fixed_length_code(2, 1),
+              cases.skewed_long_code(), cases.pairs_of([65], [1]), cases.pairs_of([1, 2, 3], [2, 2, 2])]
+    for pairs in lists:
+        host = hd.Codetable(pairs=pairs)
+        dev = hd.Codetable(device_pairs=torch.from_numpy(np.ascontiguousarray(pairs)).cuda())
+        assert (dev.min_length, dev.max_length) == (host.min_length, host.max_length)
+        assert np.array_equal(dev.blob(), host.blob())
+        host.close()
+        dev.close()
+    # malformed lists are refused: decreasing lengths, duplicate symbol, Kraft overflow
+    for bad in (cases.pairs_of([1, 2], [3, 2]), cases.pairs_of([7, 7], [1, 1]), cases.pairs_of([1, 2, 3], [1, 1, 1])):
+        with pytest.raises(hd.HDError):
+            hd.Codetable(device_pairs=torch.from_numpy(np.ascontiguousarray(bad)).cuda())
+    # and a decode through a device-built table
+    n = 500_000
+    data = O.generate(n, 0.5, seed=91)
+    pairs = hd.build_code(data, 16)
+    units, gaps, bits = hd.encode(data, pairs, want_gaps=True)
+    tab = hd.Codetable(device_pairs=torch.from_numpy(np.ascontiguousarray(pairs)).cuda())
+    d_units = hd.to_device_units(units)
+    d_gaps = torch.from_numpy(gaps.view(np.int32)).cuda()
+    dec = hd.Decoder(d_units.numel(), selfsync=False)
+    assert np.array_equal(dec.decode_gap(d_units, d_gaps, tab, n).cpu().numpy(), data)
+    tab.close()
