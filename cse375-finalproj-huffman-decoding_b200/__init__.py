@@ -50,7 +50,8 @@ ABI_SYMBOLS = [
     "hd_host_decode_selfsync", "hd_host_decode_huff", "hd_selfsync_decode_host", "hd_profile_enable",
     "hd_profile_read", "hd_launch_count", "hd_decode_selfsync_shard", "hd_set_tuning", "hd_set_trace", "hd_decode_selfsync_enqueue",
     "hd_decode_selfsync_finish", "hd_table_from_lengths_device", "hd_table_blob",
-    "hd_decode_selfsync_shard_enqueue", "hd_decode_selfsync_shard_finish",
+    "hd_decode_selfsync_shard_enqueue", "hd_decode_selfsync_shard_finish", "hd_workspace_bytes_encode",
+    "hd_histogram_device", "hd_build_code_from_histogram", "hd_encode_device",
 ]
 PROFILE_SLOTS = ("sync_chunks", "sync_seams", "decode_write", "reserved")
 
@@ -112,6 +113,11 @@ def lib():
     L.hd_profile_enable.restype = None
     L.hd_profile_read.argtypes = [vp]
     L.hd_launch_count.restype = u64
+    L.hd_workspace_bytes_encode.argtypes = [u64]
+    L.hd_workspace_bytes_encode.restype = sz
+    L.hd_histogram_device.argtypes = [vp, u64, vp, vp]
+    L.hd_build_code_from_histogram.argtypes = [vp, u32, vp, C.POINTER(u32)]
+    L.hd_encode_device.argtypes = [vp, u64, vp, u32, vp, u64, vp, u64, vp, sz, vp, vp]
     L.hd_set_tuning.argtypes = [C.c_int, C.c_int]
     L.hd_set_tuning.restype = None
     L.hd_set_trace.argtypes = [vp]
@@ -449,3 +455,35 @@ def launch_count():
 
 
 from .sharding import ShardedSelfSyncDecoder, plan_shards, place_outputs, seams_ok, resolve_seams  # noqa: E402
+
+
+def encode_device(d_data, max_len, pad_unit=False):
+    """GPU encoder (hd_histogram_device + host package-merge + hd_encode_device): uint8 CUDA tensor ->
+    (pairs, d_units int32 tensor, d_gap_words int32 tensor, total_bits).  Input side, not the hot path."""
+    torch = _torch()
+    n = d_data.numel()
+    hist = torch.zeros(256, dtype=torch.int64, device="cuda")
+    _check(lib().hd_histogram_device(d_data.data_ptr(), n, hist.data_ptr(), _stream_ptr(torch)), "hd_histogram_device")
+    h = hist.cpu().numpy().astype(np.uint64)
+    pairs = np.zeros((256, 2), dtype=np.uint8)
+    k = C.c_uint32(0)
+    _check(lib().hd_build_code_from_histogram(h.ctypes.data, max_len, pairs.ctypes.data, C.byref(k)),
+           "hd_build_code_from_histogram")
+    pairs = pairs[:k.value].copy()
+    lens = np.zeros(256, dtype=np.uint64)
+    lens[pairs[:, 0]] = pairs[:, 1]
+    bits = int((h * lens).sum())
+    n_units = (bits + 31) // 32
+    n_seg = (bits + 127) // 128
+    d_units = torch.empty(n_units + (1 if pad_unit else 0) + 4, dtype=torch.int32, device="cuda")
+    d_gaps = torch.empty((n_seg + 7) // 8 + 1, dtype=torch.int32, device="cuda")
+    nbytes = lib().hd_workspace_bytes_encode(n)
+    ws = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
+    ws_ptr = ws.data_ptr() + (-ws.data_ptr()) % 64
+    d_bits = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _check(lib().hd_encode_device(d_data.data_ptr(), n, pairs.ctypes.data, len(pairs), d_units.data_ptr(),
+                                  d_units.numel(), d_gaps.data_ptr(), d_gaps.numel(), ws_ptr, nbytes, d_bits.data_ptr(),
+                                  _stream_ptr(torch)), "hd_encode_device")
+    torch.cuda.current_stream().synchronize()
+    assert int(d_bits.item()) == bits
+    return pairs, d_units[:n_units + (1 if pad_unit else 0)], d_gaps[:(n_seg + 7) // 8], bits

@@ -13,6 +13,7 @@
 
 #include "hd_kernels.cuh"
 #include "hd_tables.cuh"
+#include "hd_encoder.cuh"
 
 using namespace hd;
 
@@ -700,6 +701,61 @@ hd_status hd_decode_selfsync(const uint32_t *d_units, uint64_t n_units, const hd
                              uint64_t n_symbols, void *d_workspace, size_t workspace_bytes, void *stream) {
     return hd_decode_selfsync_ex(d_units, n_units, 0, table, d_out, n_symbols, d_workspace, workspace_bytes,
                                  nullptr, stream);
+}
+
+// ------------------------------------------------------- device-side encoder (input side)
+size_t hd_workspace_bytes_encode(uint64_t n) {
+    const uint64_t n_tiles = std::max<uint64_t>(1, div_up(n, kEncTileSyms));
+    return 64 + 1024 + align_up(n_tiles * 8 * kStatusStride, 64);
+}
+
+hd_status hd_histogram_device(const uint8_t *d_data, uint64_t n, uint64_t *d_hist, void *stream) {
+    if (!d_data || !d_hist || n == 0) return HD_ERR_INVALID;
+    if (reinterpret_cast<uintptr_t>(d_data) & 15u) return HD_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    HD_CUDA(cudaMemsetAsync(d_hist, 0, 256 * sizeof(uint64_t), s));
+    const DeviceInfo di = device_info();
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)di.sm_count * 8, div_up(n, 256 * 16));
+    hd_histogram_kernel<<<grid ? grid : 1, 256, 0, s>>>(d_data, n, reinterpret_cast<unsigned long long *>(d_hist));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+hd_status hd_encode_device(const uint8_t *d_data, uint64_t n, const hd_sym_len *pairs, uint32_t n_pairs,
+                           uint32_t *d_units, uint64_t cap_units, uint32_t *d_gap_words, uint64_t cap_gap_words,
+                           void *d_workspace, size_t workspace_bytes, uint64_t *d_bits_out, void *stream) {
+    if (!d_data || !pairs || !d_units || !d_workspace || n == 0 || cap_units == 0) return HD_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_data) & 15u) || (reinterpret_cast<uintptr_t>(d_workspace) & 63u)) return HD_ERR_INVALID;
+    if (workspace_bytes < hd_workspace_bytes_encode(n)) return HD_ERR_WORKSPACE;
+    HostCode c;
+    if (!code_from_pairs(pairs, n_pairs, c)) return HD_ERR_FORMAT;
+    uint32_t tab[256];
+    for (int i = 0; i < 256; ++i) tab[i] = c.len[i] ? (c.code[i] | ((uint32_t)c.len[i] << 24)) : 0u;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint8_t *ws = static_cast<uint8_t *>(d_workspace);
+    EncodeParams p;
+    p.data = d_data;
+    p.n = n;
+    p.tile_counter = reinterpret_cast<uint32_t *>(ws);
+    p.code_tab = reinterpret_cast<uint32_t *>(ws + 64);
+    p.tile_status = reinterpret_cast<uint64_t *>(ws + 64 + 1024);
+    p.units = d_units;
+    p.cap_units = cap_units;
+    p.gap_words = d_gap_words;
+    p.n_tiles = div_up(n, kEncTileSyms);
+    p.bits_out = d_bits_out;
+    HD_CUDA(cudaMemsetAsync(ws, 0, hd_workspace_bytes_encode(n), s));
+    HD_CUDA(cudaMemcpyAsync(ws + 64, tab, sizeof(tab), cudaMemcpyHostToDevice, s));
+    HD_CUDA(cudaStreamSynchronize(s));   // `tab` lives on this stack frame
+    HD_CUDA(cudaMemsetAsync(d_units, 0, cap_units * 4, s));
+    if (d_gap_words) HD_CUDA(cudaMemsetAsync(d_gap_words, 0, cap_gap_words * 4, s));
+    const DeviceInfo di = device_info();
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)di.sm_count * 4, p.n_tiles);   // all resident: look-back spins
+    hd_encode_kernel<<<grid, kEncThreads, 0, s>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
 }
 
 // ------------------------------------------------------------------ tuning

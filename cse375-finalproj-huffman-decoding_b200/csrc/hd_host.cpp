@@ -237,10 +237,15 @@ hd_status hd_build_code(const uint8_t *data, uint64_t n, uint32_t max_len,
     for (auto &x : th) x.join();
     uint64_t hist[256] = {};
     for (unsigned t = 0; t < nt; ++t) for (int s = 0; s < 256; ++s) hist[s] += part[t][s];
+    return hd_build_code_from_histogram(hist, max_len, pairs_out, n_pairs_out);
+}
 
+hd_status hd_build_code_from_histogram(const uint64_t *hist, uint32_t max_len, hd_sym_len *pairs_out,
+                                       uint32_t *n_pairs_out) {
+    if (!hist || !pairs_out || !n_pairs_out || max_len == 0 || max_len > kMaxCodeLen) return HD_ERR_INVALID;
     std::vector<int> syms;
     for (int s = 0; s < 256; ++s) if (hist[s]) syms.push_back(s);
-    if (((size_t)1 << max_len) < syms.size()) return HD_ERR_INVALID;
+    if (syms.empty() || ((size_t)1 << max_len) < syms.size()) return HD_ERR_INVALID;
     std::sort(syms.begin(), syms.end(), [&](int a, int b) {
         if (hist[a] != hist[b]) return hist[a] < hist[b];
         return a > b;

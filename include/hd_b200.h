@@ -327,6 +327,29 @@ hd_status hd_huff_write(void *dst, size_t cap, const hd_sym_len *pairs,
 hd_status hd_generate(uint8_t *out, uint64_t n, double redundancy,
                       uint64_t seed, int n_threads);
 
+/* ------------------------------------------- device-side encoder (input side)
+ * Producer of the .huff payload ON THE GPU, so that inputs of any size can be
+ * made at device speed: byte histogram, then MSB-first bit packing with a
+ * single-pass look-back over bit offsets, and the 4-bit gap array.  Replaces
+ * cu_histgram/mergeHistogram, cuencoder and cu_get_gaparray
+ * (Huffman_coding_Gap_arrays/encoder/src/encoder.cu:33-116, 142-355, 358-379);
+ * the code itself is still built on the host from the 256-bin histogram
+ * (boundary package-merge there, encoder/src/package_merge.cpp:107-182).
+ * Output is bit-identical to hd_encode.  NOT the hot path.
+ *  d_data 16-byte aligned; d_units/d_gap_words are zeroed by the call;
+ *  cap_units >= ceil(bits/32) (+1 for the CUHD pad unit if wanted);
+ *  *d_bits_out (device, may be NULL) receives the total number of code bits. */
+size_t hd_workspace_bytes_encode(uint64_t n);
+hd_status hd_histogram_device(const uint8_t *d_data, uint64_t n, uint64_t *d_hist256,
+                              void *stream);
+hd_status hd_build_code_from_histogram(const uint64_t *hist256, uint32_t max_len,
+                                       hd_sym_len *pairs_out, uint32_t *n_pairs_out);
+hd_status hd_encode_device(const uint8_t *d_data, uint64_t n, const hd_sym_len *pairs,
+                           uint32_t n_pairs, uint32_t *d_units, uint64_t cap_units,
+                           uint32_t *d_gap_words, uint64_t cap_gap_words,
+                           void *d_workspace, size_t workspace_bytes,
+                           uint64_t *d_bits_out, void *stream);
+
 /* --------------------------------------------------------------- multi GPU
  * Sharding helpers (replace the naive split of gpuhd/multigpu_demo.cc:186-199).
  * Pure host arithmetic: shard `rank` of `world` over n_segments 128-bit

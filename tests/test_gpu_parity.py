@@ -489,3 +489,25 @@ def test_device_built_tables_equal_host_built(hd, torch_cuda):
     dec = hd.Decoder(d_units.numel(), selfsync=False)
     assert np.array_equal(dec.decode_gap(d_units, d_gaps, tab, n).cpu().numpy(), data)
     tab.close()
+
+
+@pytest.mark.parametrize("r", [0.0, 0.5, 0.9, 1.0])
+@pytest.mark.parametrize("n", [1, 15, 16, 4095, 4097, 1_000_003])
+def test_device_encoder_equals_host_encoder(hd, torch_cuda, r, n):
+    """histogram + pack + gap array on the GPU give, bit for bit, the host producer's payload
+    (itself checked against the oracle packer on CPU), and the payload decodes back."""
+    torch = torch_cuda
+    data = O.generate(n, r, seed=int(r * 100) + n % 97)
+    d_data = torch.from_numpy(data).cuda()
+    pairs, d_units, d_gaps, bits = hd.encode_device(d_data, 16)
+    pairs_h = hd.build_code(data, 16)
+    assert np.array_equal(pairs, pairs_h)
+    units_h, gaps_h, bits_h = hd.encode(data, pairs_h, want_gaps=True)
+    assert bits == bits_h
+    assert np.array_equal(d_units.cpu().numpy().view(np.uint32), units_h)
+    assert np.array_equal(d_gaps.cpu().numpy().view(np.uint32), gaps_h)
+    tab = hd.Codetable(pairs=pairs)
+    dec = hd.Decoder(max(d_units.numel(), 1), selfsync=False)
+    out = dec.decode_gap(d_units, d_gaps, tab, n)
+    assert np.array_equal(out.cpu().numpy(), data)
+    tab.close()
