@@ -85,6 +85,19 @@ class ClockSampler:
                 pass
             time.sleep(0.0005)
 
+    def sample(self):
+        """One synchronous sample (called right after a step has been enqueued, i.e. while the GPU executes it)."""
+        if not self.nv:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
     def start(self):
         if self.nv:
             self._t = threading.Thread(target=self._run, daemon=True)
@@ -304,6 +317,7 @@ def ours(args):
         ev[i][0].record(stream)
         step()
         ev[i][1].record(stream)
+        clocks.sample()   # NVML query while the GPU is executing this step (does not touch the stream)
         finish()   # host-side check of the step's convergence flag, after the device-timed interval
     barrier()
     launches = hd.launch_count() - launches0

@@ -20,7 +20,7 @@ constexpr uint32_t kMaxCodeLen = 16;     // .huff MAX_CODEWORD_LENGTH (decoder/i
 
 // ---- geometry of the synchronisation kernels (K1a/K1b) --------------------
 constexpr uint32_t kSyncChunkSegs = 16;  // segments per sync thread (2048 bits = two gap words)
-constexpr uint32_t kSyncHaloSegs = 4;    // segments parsed speculatively BEFORE the chunk (512 bits)
+constexpr uint32_t kSyncHaloSegs = 4;    // segments parsed speculatively BEFORE the chunk (512 bits; 6 measured: no gain)
 constexpr uint32_t kSyncWarps = 24;      // warps per persistent sync CTA (one CTA per SM)
 // A warp tile stages 32 chunks but OWNS only 31: lane 0 re-parses the last chunk of the previous tile (whose owner
 // is lane 31 there) just to hand lane 1 an exit offset that had a whole chunk to synchronise -- so the seams between
