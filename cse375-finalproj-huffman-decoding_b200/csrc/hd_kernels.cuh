@@ -224,9 +224,16 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
     __shared__ uint32_t s_total[2];
     __shared__ uint32_t s_sum[2], s_arrived[2];   // tile total / number of warps that added theirs
     __shared__ uint32_t s_ready[2];               // s_ready[b] = k+1 once the prefix of step k (buffer b) is in s_base[b]
+    __shared__ uint32_t s_t1_ready;               // the tile of step 1 is in s_tileid[1]
 
+    // Tickets: every tile id comes from the atomic counter, so tiles are only ever claimed by CTAs that are running
+    // (no assumption that the whole grid is co-resident).  The FIRST ticket is taken here, before the tables are
+    // staged, the SECOND by the scan warp after that (below): by then every CTA has its first tile, so a CTA's first
+    // look-back depends only on tiles that are decoded in the same step by the other CTAs, not on second tiles.
+    if (t == NT) s_tileid[0] = atomicAdd(p.tile_counter, 1u);
     // ---- stage the tables once per CTA (persistent) ----
     if (t < 2) { s_sum[t] = 0; s_arrived[t] = 0; s_ready[t] = 0; }
+    if (t == 0) s_t1_ready = 0;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.table.blob);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
@@ -236,16 +243,16 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             if (t < sizeof(LongTables) / 4) reinterpret_cast<uint32_t *>(s_long)[t] = __ldg(reinterpret_cast<const uint32_t *>(p.table.blob + p.table.off_long) + t);
         }
     }
-    if (t == NT) {
-        // the first two steps take static tiles, generation by generation, so that the look-back of a CTA's first
-        // tile only depends on tiles that are decoded in the SAME step by the other CTAs; later steps take tickets
-        s_tileid[0] = blockIdx.x;
-        s_tileid[1] = gridDim.x + blockIdx.x;
-    }
     __syncthreads();
 
     if (t >= NT) {
         // ======================= scan warp =======================
+        if (lane == 0) {
+            s_tileid[1] = atomicAdd(p.tile_counter, 1u);
+            __threadfence_block();
+            st_release_cta_u32(&s_t1_ready, 1u);
+        }
+        __syncwarp();
         for (uint32_t k = 0;; ++k) {
             const uint32_t b = k & 1u;
             // (slot k % 3 was written by decode thread 0 during step k-1 and is not rewritten before step k+2)
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             // round trip overlaps the look-back, but no earlier: a tile must not be claimed long before it is
             // decoded, or every higher tile's look-back waits for it.
             uint32_t ticket = 0;
-            if (lane == 0) ticket = 2u * gridDim.x + atomicAdd(p.tile_counter, 1u);
+            if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u);
             const bool tr = p.trace && blockIdx.x == kTraceCta && k < kTraceSteps && lane == 0;
             if (tr) p.trace[k * 8 + 4] = gtime_ns();
             const uint32_t wt = lane < kNW ? s_wtot[b][lane] : 0u;
@@ -421,7 +428,10 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             // barrier, so that with two output tiles no decode warp ever waits for another decode warp
             while (ld_acquire_cta_u32(&s_ready[b ^ 1u]) < k) __nanosleep(200);
         }
-        if (valid) prefetch(s_tileid[(k + 1u) % 3u]);   // from the prologue or published with s_ready above
+        if (k == 0) {
+            while (ld_acquire_cta_u32(&s_t1_ready) == 0) __nanosleep(100);   // the scan warp's second ticket
+        }
+        if (valid) prefetch(s_tileid[(k + 1u) % 3u]);   // published with s_t1_ready / s_ready above
         if (prev_valid) {
             // ---------------- finish tile k-1: compact this WARP's symbols and flush them ----------------
             const uint32_t pb = b ^ 1u;
