@@ -326,8 +326,9 @@ hd_status launch_sync_walk(const SyncLaunch &L, uint32_t *changed, cudaStream_t 
     ((L).exact ? ((L).lng ? fn<true, true>((L), __VA_ARGS__) : fn<true, false>((L), __VA_ARGS__))   \
                : ((L).lng ? fn<false, true>((L), __VA_ARGS__) : fn<false, false>((L), __VA_ARGS__)))
 
-// K1a + two K1b rounds: the first repairs chunk heads whose halo was too short, the second picks up the few group
-// seams whose predecessor's exit moved and otherwise only verifies (changed[1] == 0 <=> fixed point reached).  d_ctrl must be zeroed (kCtrlBytes) before.
+// K1a + ONE blind K1b round.  changed[0] counts the groups whose EXIT moved in that round; if it is zero every seam was
+// checked against an exit that never changed afterwards, i.e. the fixed point is reached (a second round could not
+// change anything).  d_ctrl must be zeroed (kCtrlBytes) before.
 hd_status run_sync(const SyncLaunch &L, cudaStream_t s) {
     {
         ProfScope prof(HD_PROFILE_SYNC_CHUNKS, s);
@@ -336,10 +337,8 @@ hd_status run_sync(const SyncLaunch &L, cudaStream_t s) {
     }
     if (L.p.n_chunks > 1) {
         ProfScope prof(HD_PROFILE_SYNC_SEAMS, s);
-        for (int round = 0; round < 2; ++round) {
-            hd_status st = HD_SYNC_DISPATCH(launch_sync_walk, L, L.p.changed + round, s);
-            if (st != HD_OK) return st;
-        }
+        hd_status st = HD_SYNC_DISPATCH(launch_sync_walk, L, L.p.changed, s);
+        if (st != HD_OK) return st;
     }
     return HD_OK;
 }
@@ -350,7 +349,7 @@ hd_status finish_sync(const SyncLaunch &L, cudaStream_t s, bool *extra_rounds) {
     *extra_rounds = false;
     if (L.p.n_chunks <= 1) return HD_OK;
     uint32_t h_changed = 0;
-    HD_CUDA(cudaMemcpyAsync(&h_changed, L.p.changed + 1, 4, cudaMemcpyDeviceToHost, s));
+    HD_CUDA(cudaMemcpyAsync(&h_changed, L.p.changed, 4, cudaMemcpyDeviceToHost, s));
     HD_CUDA(cudaStreamSynchronize(s));
     if (h_changed == 0) return HD_OK;
     *extra_rounds = true;
@@ -537,7 +536,7 @@ hd_status hd_selfsync_gap_array(const uint32_t *d_units, uint64_t n_units, uint3
     return HD_OK;
 }
 
-// Asynchronous half of the self-sync decode: one memset, K1a, K1b x2, K4 and the copy of the convergence counter into
+// Asynchronous half of the self-sync decode: one memset, K1a, K1b, K4 and the copy of the convergence counter into
 // *h_unconverged (pinned host memory for a truly asynchronous copy), all on `stream`; returns without synchronising.
 hd_status hd_decode_selfsync_enqueue(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit,
                                      const hd_table *table, uint8_t *d_out, uint64_t n_symbols, void *d_workspace,
@@ -552,7 +551,7 @@ hd_status hd_decode_selfsync_enqueue(const uint32_t *d_units, uint64_t n_units, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Workspace w = carve(d_workspace, n_units, true);
     const uint64_t n_seg = div_up(n_units, kSegmentUnits);
-    // K1a + K1b x2, then K4 speculatively; the convergence flag is read once at the end (the reference reads a flag
+    // K1a + K1b, then K4 speculatively; the convergence flag is read once at the end (the reference reads a flag
     // array after every phase-2 launch, cuhd_gpu_decoder.cu:461-495).  One memset covers K4's ticket counter and
     // tile statuses and, right behind them, K1's control block.
     HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes + kCtrlBytes, s));
@@ -562,11 +561,11 @@ hd_status hd_decode_selfsync_enqueue(const uint32_t *d_units, uint64_t n_units, 
     st = run_gap_decode(d_units, n_units, w.gap_words, n_seg, first_bit, table, d_out, n_symbols, w, d_count, s, 0, nullptr,
                         nullptr, true);
     if (st != HD_OK) return st;
-    if (L.p.n_chunks > 1) HD_CUDA(cudaMemcpyAsync(h_unconverged, w.changed + 1, 4, cudaMemcpyDeviceToHost, s));
+    if (L.p.n_chunks > 1) HD_CUDA(cudaMemcpyAsync(h_unconverged, w.changed, 4, cudaMemcpyDeviceToHost, s));
     return HD_OK;
 }
 
-// Synchronous half: waits for the stream; if the second blind K1b round still moved a group exit (a parse that did not
+// Synchronous half: waits for the stream; if the blind K1b round moved a group exit (a parse that did not
 // synchronise within 64 Kbit), runs further rounds to the fixed point and decodes again.
 hd_status hd_decode_selfsync_finish(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit,
                                     const hd_table *table, uint8_t *d_out, uint64_t n_symbols, void *d_workspace,
@@ -653,7 +652,7 @@ hd_status hd_decode_selfsync_shard_enqueue(const uint32_t *d_units, uint64_t n_u
     st = shard_decode(d_units, n_units_halo, n_units_shard, n_units_readable, first_bit, table, d_out, out_cap, w,
                       d_shard_info, s, true);
     if (st != HD_OK) return st;
-    if (L.p.n_chunks > 1) HD_CUDA(cudaMemcpyAsync(h_unconverged, w.changed + 1, 4, cudaMemcpyDeviceToHost, s));
+    if (L.p.n_chunks > 1) HD_CUDA(cudaMemcpyAsync(h_unconverged, w.changed, 4, cudaMemcpyDeviceToHost, s));
     return HD_OK;
 }
 

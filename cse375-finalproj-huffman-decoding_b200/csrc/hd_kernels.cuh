@@ -681,7 +681,7 @@ struct SlotSegLoader {
 // parses merge (sync_repair_chunk), carrying the exact exit into the next chunk
 // (Gauss-Seidel inside the group; no two threads ever write the same chunk).
 // `changed` counts the groups whose EXIT changed: the host launches rounds until
-// it stays zero.  Two rounds suffice unless a parse fails to synchronise within a
+// it stays zero.  One round suffices unless a parse fails to synchronise within a
 // whole group (64 Kbit); a code that never synchronises (all codewords the same
 // length not dividing 128) advances one group per round -- the true parse of
 // such a code is inherently sequential; this is the graceful worst case, the

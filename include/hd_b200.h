@@ -122,7 +122,7 @@ hd_status hd_decode_selfsync(const uint32_t *d_units, uint64_t n_units,
                              size_t workspace_bytes, void *stream);
 
 /* The same decode split in two for callers that overlap it with other work:
- * _enqueue puts everything (one memset, K1a, K1b x2, K4, the 4-byte copy of
+ * _enqueue puts everything (one memset, K1a, K1b, K4, the 4-byte copy of
  * the convergence counter into *h_unconverged -- pinned host memory) on
  * `stream` and returns without synchronising; _finish synchronises the stream
  * and, in the rare case that *h_unconverged != 0 (a parse that did not

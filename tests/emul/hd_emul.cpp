@@ -229,7 +229,7 @@ static int64_t emul_sync_t(HostTables &h, const uint32_t *units, uint64_t n_unit
     for (uint64_t i = 0; i < n_chunks * kW; ++i) gap_words_out[i] = fin_words[i];
     ent = fin_ent;
     for (uint64_t c = 0; c < n_chunks; ++c) cur_entry[c] = (uint8_t)ent[c];
-    // ---- K1b rounds: two blind ones, then until no group exit changes ----
+    // ---- K1b rounds: one blind round, then further ones until no group exit changes ----
     if (rounds_out) { rounds_out[0] = 0; rounds_out[1] = 0; }
     int64_t rounds = 0;
     const uint64_t n_groups = (n_chunks + kSyncWalkChunksEmul - 1) / kSyncWalkChunksEmul;
@@ -261,7 +261,7 @@ static int64_t emul_sync_t(HostTables &h, const uint32_t *units, uint64_t n_unit
         }
         ++rounds;
         if (rounds_out) rounds_out[1] += 1;
-        if (!ch && rounds >= 2) return rounds;
+        if (!ch) return rounds;
     }
     return -2;
 }
