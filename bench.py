@@ -393,7 +393,10 @@ def ours(args):
         "config": {"workload": WORKLOAD, "scheme": "selfsync", "mib_per_gpu": args.mib, "redundancy": args.redundancy,
                    "subsequence_bits": 128, "max_codeword_length": 11, "n_symbols_total": int(n_total),
                    "n_units_total": int(len(units)), "l2": "flushed between steps (256 MiB write, outside the events)",
-                   "parallelism": "shard%d" % world},
+                   "parallelism": "shard%d" % world,
+                   "exchange": ("none" if world == 1 else
+                                "peer-memory mailbox over NVLink (hd_mailbox_*)" if shard.mailbox is not None else
+                                "ncclAllGather of 24 B")},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity": "byte-exact",
     }
     if rank == 0:
@@ -409,6 +412,8 @@ def ours(args):
                 pass
     elif dist is not None:
         barrier()
+    if shard is not None:
+        shard.close()
     table.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -51,7 +51,9 @@ ABI_SYMBOLS = [
     "hd_profile_read", "hd_launch_count", "hd_decode_selfsync_shard", "hd_set_tuning", "hd_set_trace", "hd_decode_selfsync_enqueue",
     "hd_decode_selfsync_finish", "hd_table_from_lengths_device", "hd_table_blob",
     "hd_decode_selfsync_shard_enqueue", "hd_decode_selfsync_shard_finish", "hd_workspace_bytes_encode",
-    "hd_histogram_device", "hd_build_code_from_histogram", "hd_encode_device",
+    "hd_histogram_device", "hd_build_code_from_histogram", "hd_encode_device", "hd_mailbox_create",
+    "hd_mailbox_export", "hd_mailbox_connect", "hd_mailbox_publish", "hd_mailbox_wait", "hd_mailbox_timed_out",
+    "hd_mailbox_destroy",
 ]
 PROFILE_SLOTS = ("sync_chunks", "sync_seams", "decode_write", "reserved")
 
@@ -113,6 +115,15 @@ def lib():
     L.hd_profile_enable.restype = None
     L.hd_profile_read.argtypes = [vp]
     L.hd_launch_count.restype = u64
+    L.hd_mailbox_create.argtypes = [u32, u32, C.POINTER(vp)]
+    L.hd_mailbox_export.argtypes = [vp, vp]
+    L.hd_mailbox_connect.argtypes = [vp, vp]
+    L.hd_mailbox_publish.argtypes = [vp, vp, u64, vp]
+    L.hd_mailbox_wait.argtypes = [vp, u64, vp, vp]
+    L.hd_mailbox_timed_out.argtypes = [vp]
+    L.hd_mailbox_timed_out.restype = C.c_int
+    L.hd_mailbox_destroy.argtypes = [vp]
+    L.hd_mailbox_destroy.restype = None
     L.hd_workspace_bytes_encode.argtypes = [u64]
     L.hd_workspace_bytes_encode.restype = sz
     L.hd_histogram_device.argtypes = [vp, u64, vp, vp]

@@ -14,6 +14,7 @@
 #include "hd_kernels.cuh"
 #include "hd_tables.cuh"
 #include "hd_encoder.cuh"
+#include "hd_mailbox.cuh"
 
 using namespace hd;
 
@@ -755,6 +756,97 @@ hd_status hd_encode_device(const uint8_t *d_data, uint64_t n, const hd_sym_len *
     g_launches.fetch_add(1, std::memory_order_relaxed);
     HD_CUDA(cudaGetLastError());
     return HD_OK;
+}
+
+// ------------------------------------------------------ multi-GPU mailbox (peer-memory exchange over NVLink)
+struct hd_mailbox {
+    uint32_t world = 0, rank = 0;
+    int device = 0;
+    unsigned long long *local = nullptr;
+    MailboxPeers peers = {};
+    bool opened[kMailboxMaxWorld] = {};
+    uint32_t *d_timeout = nullptr;
+};
+
+void hd_mailbox_destroy(hd_mailbox *m) {
+    if (!m) return;
+    for (uint32_t p = 0; p < m->world; ++p)
+        if (m->opened[p]) cudaIpcCloseMemHandle(m->peers.buf[p]);
+    if (m->local) cudaFree(m->local);
+    if (m->d_timeout) cudaFree(m->d_timeout);
+    delete m;
+}
+
+hd_status hd_mailbox_create(uint32_t world, uint32_t rank, hd_mailbox **out) {
+    if (!out || world == 0 || world > kMailboxMaxWorld || rank >= world) return HD_ERR_INVALID;
+    hd_mailbox *m = new (std::nothrow) hd_mailbox();
+    if (!m) return HD_ERR_INVALID;
+    m->world = world;
+    m->rank = rank;
+    cudaError_t e = cudaGetDevice(&m->device);
+    const size_t bytes = (size_t)world * kMailboxSlotWords * 8;
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&m->local), bytes);
+    if (e == cudaSuccess) e = cudaMemset(m->local, 0, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&m->d_timeout), 4);
+    if (e == cudaSuccess) e = cudaMemset(m->d_timeout, 0, 4);
+    if (e != cudaSuccess) {
+        g_last_cuda = e;
+        (void)cudaGetLastError();
+        hd_mailbox_destroy(m);
+        return HD_ERR_CUDA;
+    }
+    m->peers.buf[rank] = m->local;
+    *out = m;
+    return HD_OK;
+}
+
+hd_status hd_mailbox_export(hd_mailbox *m, uint8_t handle_out[64]) {
+    if (!m || !handle_out) return HD_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    HD_CUDA(cudaIpcGetMemHandle(&h, m->local));
+    std::memcpy(handle_out, &h, 64);
+    return HD_OK;
+}
+
+hd_status hd_mailbox_connect(hd_mailbox *m, const uint8_t *handles) {
+    if (!m || !handles) return HD_ERR_INVALID;
+    for (uint32_t p = 0; p < m->world; ++p) {
+        if (p == m->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + (size_t)p * 64, 64);
+        void *ptr = nullptr;
+        HD_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        m->peers.buf[p] = static_cast<unsigned long long *>(ptr);
+        m->opened[p] = true;
+    }
+    return HD_OK;
+}
+
+hd_status hd_mailbox_publish(hd_mailbox *m, const uint64_t *d_info3, uint64_t seq, void *stream) {
+    if (!m || !d_info3 || seq == 0) return HD_ERR_INVALID;
+    hd_mailbox_publish_kernel<<<1, kMailboxMaxWorld, 0, static_cast<cudaStream_t>(stream)>>>(
+        m->peers, m->world, m->rank, reinterpret_cast<const unsigned long long *>(d_info3), seq);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+hd_status hd_mailbox_wait(hd_mailbox *m, uint64_t seq, uint64_t *d_all_info3, void *stream) {
+    if (!m || !d_all_info3 || seq == 0) return HD_ERR_INVALID;
+    hd_mailbox_wait_kernel<<<1, kMailboxMaxWorld, 0, static_cast<cudaStream_t>(stream)>>>(
+        m->local, m->world, seq, reinterpret_cast<unsigned long long *>(d_all_info3), m->d_timeout);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+// 1 if a wait gave up because a peer never published (checked by the caller after it synchronised the stream)
+int hd_mailbox_timed_out(hd_mailbox *m) {
+    if (!m) return 1;
+    uint32_t v = 0;
+    if (cudaMemcpy(&v, m->d_timeout, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    return v != 0;
 }
 
 // ------------------------------------------------------------------ tuning

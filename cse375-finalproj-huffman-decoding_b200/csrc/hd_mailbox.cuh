@@ -1,0 +1,64 @@
+// hd_mailbox.cuh -- the multi-GPU exchange of the shard decode as peer-memory stores over NVLink instead of an NCCL
+// call: every rank owns a small "mailbox" in its HBM (one 32-byte slot per rank), opened by all peers through CUDA
+// IPC.  After its decode a rank PUSHES {symbols decoded, entry offset, exit offset, sequence number} into its slot of
+// every peer's mailbox (one tiny kernel, st.release.sys); a rank has the all-gather as soon as every slot of its own
+// mailbox carries the current sequence number (one tiny kernel, ld.acquire.sys).  ~3 us instead of ~40 us for an
+// 8-rank ncclAllGather of 24 bytes, and no host involvement.  (the exchange is 8-16 B per GPU.)
+#ifndef HD_MAILBOX_CUH_
+#define HD_MAILBOX_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hd {
+
+constexpr uint32_t kMailboxSlotWords = 4;      // {count, entry, exit, seq}
+constexpr uint32_t kMailboxMaxWorld = 64;
+
+struct MailboxPeers {
+    unsigned long long *buf[kMailboxMaxWorld];   // buf[p] = base of rank p's mailbox (peer-mapped; own entry = local)
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// thread p writes this rank's info into slot `rank` of rank p's mailbox
+__global__ void hd_mailbox_publish_kernel(MailboxPeers peers, uint32_t world, uint32_t rank, const unsigned long long *info3,
+                                          unsigned long long seq) {
+    const uint32_t p = threadIdx.x;
+    if (p >= world) return;
+    unsigned long long *slot = peers.buf[p] + (size_t)rank * kMailboxSlotWords;
+    slot[0] = info3[0];
+    slot[1] = info3[1];
+    slot[2] = info3[2];
+    __threadfence_system();
+    st_release_sys_u64(slot + 3, seq);
+}
+
+// thread p waits for slot p of the local mailbox and copies it out; *timeout is set if a peer never shows up
+__global__ void hd_mailbox_wait_kernel(const unsigned long long *local, uint32_t world, unsigned long long seq,
+                                       unsigned long long *all_info3, uint32_t *timeout) {
+    const uint32_t p = threadIdx.x;
+    if (p >= world) return;
+    const unsigned long long *slot = local + (size_t)p * kMailboxSlotWords;
+    unsigned long long spins = 0;
+    while (ld_acquire_sys_u64(slot + 3) < seq) {
+        __nanosleep(200);
+        if (++spins > 50000000ull) {   // ~10 s: a peer died; do not hang the GPU
+            if (timeout) *timeout = 1;
+            return;
+        }
+    }
+    all_info3[p * 3 + 0] = slot[0];
+    all_info3[p * 3 + 1] = slot[1];
+    all_info3[p * 3 + 2] = slot[2];
+}
+
+}  // namespace hd
+#endif  // HD_MAILBOX_CUH_

@@ -74,7 +74,9 @@ def resolve_seams(rank, world, infos, gather, redecode, n_symbols):
 class ShardedSelfSyncDecoder:
     """One rank's shard of a self-synchronising decode (CUDA)."""
 
-    def __init__(self, units, table, n_symbols, rank, world, dist=None, halo_segments=HALO_SEGMENTS):
+
+    def __init__(self, units, table, n_symbols, rank, world, dist=None, halo_segments=HALO_SEGMENTS,
+                 use_mailbox=True):
         import torch
         from . import lib, _check, _stream_ptr
         self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
@@ -106,6 +108,54 @@ class ShardedSelfSyncDecoder:
         self.offset = 0
         self._flag = None
         self._pending = None
+        # the per-step exchange: peer-memory mailbox over NVLink (hd_mailbox_*) if CUDA IPC works between all ranks,
+        # else an NCCL all-gather of the same 24 bytes
+        self.mailbox = None
+        self.seq = 0
+        if dist is not None and world > 1 and use_mailbox:
+            self._setup_mailbox()
+
+    def _setup_mailbox(self):
+        torch, L = self.torch, self._lib
+        h = C.c_void_p(None)
+        ok = L.hd_mailbox_create(self.world, self.rank, C.byref(h)) == 0
+        handle = np.zeros(64, dtype=np.uint8)
+        if ok:
+            ok = L.hd_mailbox_export(h, handle.ctypes.data) == 0
+        mine = torch.from_numpy(handle).cuda()
+        every = torch.zeros(64 * self.world, dtype=torch.uint8, device="cuda")
+        self.dist.all_gather_into_tensor(every, mine)
+        if ok:
+            handles = np.ascontiguousarray(every.cpu().numpy())
+            ok = L.hd_mailbox_connect(h, handles.ctypes.data) == 0
+        t = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)      # all ranks or none
+        if int(t.item()):
+            self.mailbox = h
+        elif h:
+            L.hd_mailbox_destroy(h)
+
+    def _exchange(self):
+        """All-gather of self.info into self.all_info, on the stream (collective: every rank calls it)."""
+        if self.mailbox is not None:
+            self.seq += 1
+            sp = self._stream_ptr(self.torch)
+            self._check(self._lib.hd_mailbox_publish(self.mailbox, C.c_void_p(self.info.data_ptr()), self.seq, sp),
+                        "hd_mailbox_publish")
+            self._check(self._lib.hd_mailbox_wait(self.mailbox, self.seq, C.c_void_p(self.all_info.data_ptr()), sp),
+                        "hd_mailbox_wait")
+        elif self.dist is not None and self.world > 1:
+            self.dist.all_gather_into_tensor(self.all_info, self.info)
+        else:
+            self.all_info.copy_(self.info)
+
+    def close(self):
+        if self.mailbox is not None:
+            self.torch.cuda.synchronize()
+            if self.dist is not None:
+                self.dist.barrier()          # nobody may still be writing into a mailbox that is about to go
+            self._lib.hd_mailbox_destroy(self.mailbox)
+            self.mailbox = None
 
     def _args(self, first_bit, halo):
         hu = self.n_units_halo if halo else 0
@@ -126,10 +176,7 @@ class ShardedSelfSyncDecoder:
             self._flag = self.torch.zeros(16, dtype=self.torch.int32).pin_memory()
         self._pending = self._args(0, True) + (C.c_void_p(self._flag.data_ptr()), self._stream_ptr(self.torch))
         self._check(self._lib.hd_decode_selfsync_shard_enqueue(*self._pending), "hd_decode_selfsync_shard_enqueue")
-        if self.dist is not None and self.world > 1:
-            self.dist.all_gather_into_tensor(self.all_info, self.info)
-        else:
-            self.all_info.copy_(self.info)
+        self._exchange()
 
     def wait(self):
         """Host half of a step: synchronise; in the rare unconverged case finish the synchronisation, decode again
@@ -144,15 +191,15 @@ class ShardedSelfSyncDecoder:
             t = self.torch.tensor([redone], dtype=self.torch.int64, device="cuda")
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             if int(t.item()):
-                self.dist.all_gather_into_tensor(self.all_info, self.info)
+                self._exchange()
+                self.torch.cuda.current_stream().synchronize()
         elif redone:
             self.all_info.copy_(self.info)
+        if self.mailbox is not None and self._lib.hd_mailbox_timed_out(self.mailbox):
+            raise RuntimeError("shard exchange timed out: a peer rank never published its counts")
 
     def _gather(self):
-        if self.dist is not None and self.world > 1:
-            self.dist.all_gather_into_tensor(self.all_info, self.info)
-        else:
-            self.all_info.copy_(self.info)
+        self._exchange()
         return self.all_info.cpu().numpy().reshape(self.world, 3)
 
     def finish(self):

@@ -357,6 +357,28 @@ hd_status hd_encode_device(const uint8_t *d_data, uint64_t n, const hd_sym_len *
 void hd_shard_segments(uint64_t n_segments, uint32_t rank, uint32_t world,
                        uint64_t *seg_begin, uint64_t *seg_end);
 
+/* Mailbox: the per-step exchange of {count, entry, exit} between the ranks of
+ * a sharded decode, done with peer-memory stores over NVLink / NVSwitch (CUDA
+ * IPC) instead of a collective call: publish = one tiny kernel that writes
+ * this rank's triple + a sequence number into its slot of EVERY peer's
+ * mailbox; wait = one tiny kernel that returns once all slots of the local
+ * mailbox carry that sequence number and copies the world x 3 values out.
+ * Set-up (once): create on every rank, exchange the 64-byte handles by any
+ * means (e.g. torch.distributed all_gather), connect.  seq must increase by
+ * one per step and start at 1.  Replaces the host-side stitching of
+ * gpuhd/multigpu_demo.cc:301-313; an ncclAllGather of the same 24 bytes is the
+ * fallback (`sharding.py`). */
+typedef struct hd_mailbox hd_mailbox;
+hd_status hd_mailbox_create(uint32_t world, uint32_t rank, hd_mailbox **out);
+hd_status hd_mailbox_export(hd_mailbox *m, uint8_t handle_out[64]);
+hd_status hd_mailbox_connect(hd_mailbox *m, const uint8_t *handles /* world x 64 */);
+hd_status hd_mailbox_publish(hd_mailbox *m, const uint64_t *d_info3, uint64_t seq,
+                             void *stream);
+hd_status hd_mailbox_wait(hd_mailbox *m, uint64_t seq, uint64_t *d_all_info3,
+                          void *stream);
+int hd_mailbox_timed_out(hd_mailbox *m);
+void hd_mailbox_destroy(hd_mailbox *m);
+
 #ifdef __cplusplus
 }
 #endif

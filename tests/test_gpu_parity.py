@@ -511,3 +511,28 @@ def test_device_encoder_equals_host_encoder(hd, torch_cuda, r, n):
     out = dec.decode_gap(d_units, d_gaps, tab, n)
     assert np.array_equal(out.cpu().numpy(), data)
     tab.close()
+
+
+def test_mailbox_single_rank_roundtrip(hd, torch_cuda):
+    """hd_mailbox_* with world 1 (the multi-rank path runs under torchrun in bench.py): publish + wait move the triple
+    into the gathered array, sequence numbers gate the wait."""
+    import ctypes as C
+    torch = torch_cuda
+    L = hd.lib()
+    h = C.c_void_p(None)
+    assert L.hd_mailbox_create(1, 0, C.byref(h)) == 0
+    handle = np.zeros(64, dtype=np.uint8)
+    assert L.hd_mailbox_export(h, handle.ctypes.data) == 0
+    assert L.hd_mailbox_connect(h, handle.ctypes.data) == 0
+    info = torch.tensor([123456789012, 7, 9], dtype=torch.int64, device="cuda")
+    allinfo = torch.zeros(3, dtype=torch.int64, device="cuda")
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for seq in (1, 2, 3):
+        info[0] += 1
+        assert L.hd_mailbox_publish(h, C.c_void_p(info.data_ptr()), seq, sp) == 0
+        assert L.hd_mailbox_wait(h, seq, C.c_void_p(allinfo.data_ptr()), sp) == 0
+        torch.cuda.synchronize()
+        assert allinfo.tolist() == info.tolist()
+    assert L.hd_mailbox_timed_out(h) == 0
+    assert L.hd_mailbox_publish(h, C.c_void_p(info.data_ptr()), 0, sp) != 0     # seq 0 is reserved
+    L.hd_mailbox_destroy(h)
