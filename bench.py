@@ -277,8 +277,10 @@ def ours(args):
     else:
         from hd_b200 import ShardedSelfSyncDecoder
         shard = ShardedSelfSyncDecoder(units, table, n_total, rank, world, dist=dist)
-        step = shard.step      # enqueue the shard decode + the NCCL all-gather, no host synchronisation
-        finish = shard.wait    # stream sync + convergence flag (collective only if some rank had to decode again)
+        step = shard.step      # enqueue the shard decode + the exchange of the counts, no host synchronisation
+
+        def finish():          # the sharded steps are checked together after the timed loop (shard.wait): a host
+            pass               # sync per step would put the launch skew between the 8 processes into every step
 
     flush = torch.zeros(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
@@ -292,6 +294,8 @@ def ours(args):
         flush.add_(1)
         step()
         finish()
+    if shard is not None:
+        shard.wait()
     barrier()
 
     # -------- parity of what we are about to time (outside the timed region)
@@ -317,8 +321,12 @@ def ours(args):
         ev[i][0].record(stream)
         step()
         ev[i][1].record(stream)
-        clocks.sample()   # NVML query while the GPU is executing this step (does not touch the stream)
+        if world == 1:
+            clocks.sample()   # NVML query while the GPU is executing this step (does not touch the stream); at N > 1
+                              # the steps are enqueued back to back and only the sampler thread watches the clocks
         finish()   # host-side check of the step's convergence flag, after the device-timed interval
+    if shard is not None:
+        shard.wait()          # stream sync + the steps' convergence flags (collective if some rank decoded again)
     barrier()
     launches = hd.launch_count() - launches0
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -339,6 +347,8 @@ def ours(args):
         for k, v in hd.profile_read().items():
             kern[k] += v / args.steps
     hd.profile_enable(False)
+    if shard is not None:
+        shard.wait()
     barrier()
     clk = clocks.stop()   # sampled over the timed region and the per-kernel pass of the same workload
     if world == 1:

@@ -107,7 +107,8 @@ class ShardedSelfSyncDecoder:
         self.count_local = 0
         self.offset = 0
         self._flag = None
-        self._pending = None
+        self._outstanding = []
+        self._next_slot = 0
         # the per-step exchange: peer-memory mailbox over NVLink (hd_mailbox_*) if CUDA IPC works between all ranks,
         # else an NCCL all-gather of the same 24 bytes
         self.mailbox = None
@@ -171,22 +172,34 @@ class ShardedSelfSyncDecoder:
 
     def step(self):
         """The timed step, entirely on the stream: local shard decode (hd_decode_selfsync_shard_enqueue) + the
-        all-gather of {count, entry, exit}.  Call wait() before using the results."""
+        exchange of {count, entry, exit}.  Several steps may be enqueued back to back (each has its own convergence
+        flag, up to 16 outstanding); call wait() before using the results."""
         if self._flag is None:
             self._flag = self.torch.zeros(16, dtype=self.torch.int32).pin_memory()
-        self._pending = self._args(0, True) + (C.c_void_p(self._flag.data_ptr()), self._stream_ptr(self.torch))
-        self._check(self._lib.hd_decode_selfsync_shard_enqueue(*self._pending), "hd_decode_selfsync_shard_enqueue")
+        if len(self._outstanding) >= 16:
+            self.wait()
+        slot = self._next_slot
+        self._next_slot = (slot + 1) % 16
+        self._outstanding.append(slot)
+        args = self._args(0, True) + (C.c_void_p(self._flag.data_ptr() + 4 * slot), self._stream_ptr(self.torch))
+        self._check(self._lib.hd_decode_selfsync_shard_enqueue(*args), "hd_decode_selfsync_shard_enqueue")
         self._exchange()
 
     def wait(self):
-        """Host half of a step: synchronise; in the rare unconverged case finish the synchronisation, decode again
-        and re-gather (hd_decode_selfsync_shard_finish)."""
-        if self._pending is None:
+        """Host half of the enqueued steps: synchronise the stream and look at their convergence flags.  In the rare
+        unconverged case (a parse that did not synchronise within 64 Kbit) the shard is decoded again synchronously
+        (iterating the synchronisation to its fixed point) and the counts are exchanged again."""
+        if not self._outstanding:
             return
-        self._check(self._lib.hd_decode_selfsync_shard_finish(*self._pending), "hd_decode_selfsync_shard_finish")
-        redone = int(self._flag[0].item())
-        self._pending = None
-        # every rank must take part in a re-gather if ANY rank had to decode again
+        self.torch.cuda.current_stream().synchronize()
+        redone = 0
+        for slot in self._outstanding:
+            if int(self._flag[slot].item()):
+                redone = 1
+        self._outstanding = []
+        if redone:
+            self._decode()
+        # every rank must take part in a re-exchange if ANY rank had to decode again
         if self.dist is not None and self.world > 1:
             t = self.torch.tensor([redone], dtype=self.torch.int64, device="cuda")
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
