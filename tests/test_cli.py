@@ -73,3 +73,30 @@ def test_reference_demo_source_runs_on_our_library(tmp_path):
                os.environ.get("LD_LIBRARY_PATH", ""))
     out = subprocess.run([exe, "0", "16"], cwd=work, capture_output=True, text=True, check=True, env=env).stdout
     assert "Decompression throughput (mb/s):" in out and "mismatch" not in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("r", [0.5, 0.75, 0.9])
+def test_decode_huff_written_by_the_reference_gpu_encoder(hd, tmp_path, r):
+    """Interoperability of the container: a .huff produced by the UNMODIFIED reference encoder
+    (Huffman_coding_Gap_arrays/encoder, rebuilt for sm_100 by oracle/Makefile) is decoded by our decoder -- both
+    through the library and through bin/decoder -- to the original bytes.  (The reference's own decoder is wrong for
+    maximum code lengths below 10, SURVEY D7, which is why r starts at 0.5 only for OUR side.)"""
+    enc = os.path.join(ROOT, "oracle", "_ref", "gap_encoder")
+    if not os.path.exists(enc):
+        pytest.skip("oracle/_ref/gap_encoder not built (needs /root/reference at build time)")
+    n = 4_000_003
+    data = O.generate(n, r, seed=int(r * 100))
+    data.tofile(tmp_path / "in.bin")
+    run = subprocess.run([enc, str(tmp_path / "in.bin"), str(tmp_path / "ref.huff")], capture_output=True, text=True)
+    if run.returncode != 0 or not (tmp_path / "ref.huff").exists():
+        pytest.skip("the reference encoder does not run on this GPU: " + (run.stderr or run.stdout)[-200:])
+    image = np.fromfile(tmp_path / "ref.huff", dtype=np.uint8)
+    hf = hd.HuffFile(image)
+    assert hf.original_size == n
+    got, _ = hd.decode_huff(image, device=0)
+    assert np.array_equal(got, data)
+    assert np.array_equal(O.huff_decode(image, n), data)            # and the oracle agrees on the reference's file
+    dec = _need("decoder")
+    subprocess.run([dec, str(tmp_path / "ref.huff"), str(tmp_path / "out.bin")], check=True, capture_output=True)
+    assert np.array_equal(np.fromfile(tmp_path / "out.bin", dtype=np.uint8), data)
