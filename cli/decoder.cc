@@ -1,10 +1,11 @@
 // decoder.cc -- `./bin/decoder <input.huff> <decoded_file>`
 // CLI shape and output lines of the reference gap-array decoder (Huffman_coding_Gap_arrays/decoder/src/huff.cpp:
 // 31-129, decoder.cu:803-808), written fresh over hd_b200.h.  Differences on purpose: the second argument
-// is honoured, the kernel runs once instead of 200 times, nothing is written past the original size.
+// is honoured, the decode runs 20 times (HD_DECODER_LOOP) instead of 200, nothing is written past the original size.
 #include <cuda_runtime.h>
 #include <hd_b200.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -12,6 +13,18 @@
 
 static void fatal(const char *msg) {
     std::fprintf(stderr, "%s\n", msg);
+    std::exit(EXIT_FAILURE);
+}
+
+static void check(hd_status st) {
+    if (st == HD_OK) return;
+    std::fprintf(stderr, "decode failed: %s (%s)\n", hd_status_string(st), hd_last_cuda_error());
+    std::exit(EXIT_FAILURE);
+}
+
+static void cuda_check(cudaError_t e) {
+    if (e == cudaSuccess) return;
+    std::fprintf(stderr, "CUDA error: %s\n", cudaGetErrorString(e));
     std::exit(EXIT_FAILURE);
 }
 
@@ -38,16 +51,50 @@ int main(int argc, char **argv) {
 
     void *out = nullptr;
     if (cudaMallocHost(&out, (size_t)v.original_size + 16) != cudaSuccess) fatal("cudaMallocHost failed");
+    const size_t out_size = v.original_size;
+    // The reference runs each stage LOOP*2 = 200 times and prints the mean of the second half (decoder.cu:760-803);
+    // here the copies run once and the decode launch HD_DECODER_LOOP*2 times (default 10+10) with the same averaging,
+    // so `dec` is a warm figure on both sides.
+    int loop = 10;
+    if (const char *e = std::getenv("HD_DECODER_LOOP")) loop = std::max(1, std::atoi(e));
     float ms[3] = {0, 0, 0};
-    size_t out_size = 0;
     const auto t0 = std::chrono::high_resolution_clock::now();
-    const hd_status st = hd_huff_decode_host(image, (size_t)fsize, static_cast<uint8_t *>(out),
-                                             (size_t)v.original_size + 16, &out_size, 0, ms);
-    const auto t1 = std::chrono::high_resolution_clock::now();
-    if (st != HD_OK) {
-        std::fprintf(stderr, "decode failed: %s (%s)\n", hd_status_string(st), hd_last_cuda_error());
-        return EXIT_FAILURE;
+    if (v.original_size && v.n_units) {
+        hd_table *tab = nullptr;
+        check(hd_table_from_lengths(v.symbols, (uint32_t)v.symbol_count, nullptr, &tab));
+        const size_t gap_words = ((size_t)v.n_segments + 7) / 8;
+        const size_t gap_bytes = (gap_words * 4 + 255) / 256 * 256;   // units start 256-byte aligned behind the gap words
+        const size_t ws_bytes = hd_workspace_bytes_gap(v.n_units);
+        uint8_t *d_in = nullptr, *d_out = nullptr;
+        void *d_ws = nullptr;
+        cuda_check(cudaMalloc(reinterpret_cast<void **>(&d_in), gap_bytes + (size_t)v.n_units * 4 + 256));
+        cuda_check(cudaMalloc(reinterpret_cast<void **>(&d_out), (size_t)v.original_size + 256));
+        cuda_check(cudaMalloc(&d_ws, ws_bytes));
+        cudaEvent_t ev[5];   // start, H2D done, timed half starts, decodes done, D2H done
+        for (auto &e : ev) cuda_check(cudaEventCreate(&e));
+        cuda_check(cudaEventRecord(ev[0]));
+        cuda_check(cudaMemcpyAsync(d_in, v.gap_words, gap_words * 4, cudaMemcpyHostToDevice));
+        cuda_check(cudaMemcpyAsync(d_in + gap_bytes, v.units, (size_t)v.n_units * 4, cudaMemcpyHostToDevice));
+        cuda_check(cudaEventRecord(ev[1]));
+        for (int i = 0; i < loop * 2; ++i) {
+            if (i == loop) cuda_check(cudaEventRecord(ev[2]));
+            check(hd_decode_gap(reinterpret_cast<const uint32_t *>(d_in + gap_bytes), v.n_units,
+                                reinterpret_cast<const uint32_t *>(d_in), v.n_segments, tab, d_out, v.original_size,
+                                d_ws, ws_bytes, nullptr));
+        }
+        cuda_check(cudaEventRecord(ev[3]));
+        cuda_check(cudaMemcpyAsync(out, d_out, v.original_size, cudaMemcpyDeviceToHost));
+        cuda_check(cudaEventRecord(ev[4]));
+        cuda_check(cudaEventSynchronize(ev[4]));
+        cuda_check(cudaEventElapsedTime(&ms[0], ev[0], ev[1]));
+        cuda_check(cudaEventElapsedTime(&ms[1], ev[2], ev[3]));
+        ms[1] /= (float)loop;
+        cuda_check(cudaEventElapsedTime(&ms[2], ev[3], ev[4]));
+        cudaFree(d_in); cudaFree(d_out); cudaFree(d_ws);
+        for (auto &e : ev) cudaEventDestroy(e);
+        hd_table_free(tab);
     }
+    const auto t1 = std::chrono::high_resolution_clock::now();
     std::printf("HtoD,%f, dec,%f, DtoH,%f,SEGMENTSIZE,128,THREAD_NUM,512,LOCAL_SEGMENT_NUM,2\n", ms[0], ms[1], ms[2]);
     const double total_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     std::printf("Decode time: %.3f ms\n", total_ms);
