@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhd_b200.so")
+LIB_PATH = os.environ.get("HD_B200_LIB") or os.path.join(_HERE, "libhd_b200.so")   # override: developer builds only
 
 HD_OK = 0
 SEGMENT_UNITS = 4      # 128-bit subsequence / segment (gpuhd/src/demo.cc:16, encoder/include/constants.hpp:12)

@@ -15,6 +15,10 @@
 #define HD_HD inline
 #endif
 
+#ifndef HD_WHATIF
+#define HD_WHATIF 0   // developer timing experiments (tools/whatif.sh); 0 in every shipped build
+#endif
+
 namespace hd {
 
 // upper 32 bits of (hi:lo) << (s & 31)
@@ -44,6 +48,7 @@ struct DecodeTables {
     const uint32_t *lut;     // primary multi-symbol LUT {sym0, sym1, bits, count}
     uint32_t idx_shift;      // 32 - lut_bits
     uint32_t lut_bits;
+    uint32_t one;            // the constant 1, opaque to the compiler (see decode_chunk)
     const uint8_t *len_tab;  // code length by symbol
     const LongTables *lt;
     const uint8_t *order;
@@ -103,8 +108,12 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
     constexpr uint32_t kColBits = col_bits(NT);
     static_assert(row_shift(NT) != 0, "unsupported tile width");
     uint32_t w0 = in_col[0], w1 = in_col[NT];
+    uint32_t w2 = in_col[2 * NT];
+#if defined(__CUDA_ARCH__)
+    uint32_t nxt = (uint32_t)__cvta_generic_to_shared(in_col + 2 * NT);   // shared-window address of the word in w2
+#else
     const uint32_t *nxt = in_col + 2 * NT;
-    uint32_t w2 = *nxt;
+#endif
     const uint32_t col = stage_addr & kColBits;
     uint32_t A = stage_addr;
     uint32_t pos = entry;
@@ -116,23 +125,39 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
             if ((e >> 16) == 0) e = resolve_long(win, T.lut_bits, T.lt, T.order);
         }
         const uint32_t u = A | kColBits;
+#if !(HD_WHATIF & 2)
         smem_st_u8(A, e, arena);
         smem_st_u8(((u + 1u) & ~kColBits) | col, e >> 8, arena);
+#endif
         A = ((u + (e >> 24)) & ~kColBits) | col;
         const uint32_t np = pos + byte2(e);
-        if ((np ^ pos) & 32u) {   // crossed a unit boundary: slide the window
+#if defined(__CUDA_ARCH__)
+        // Crossed a unit boundary: slide the window and fetch the word after it.  One asm block with its own predicate,
+        // so that the slide stays predicated moves (FMA pipe; the INT pipe bounds this loop) and the load writes w2 IN
+        // PLACE: it is consumed by the next slide, at least two lookups later, so its latency never sits on the
+        // loop-carried path and it costs a shared-memory wavefront once per unit instead of once per lookup.
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 x;\n\t"
+            "xor.b32 x, %4, %5;\n\t"
+            "and.b32 x, x, 32;\n\t"
+            "setp.ne.u32 p, x, 0;\n\t"
+            "@p mad.lo.u32 %0, %1, %6, 0;\n\t"    // w0 = w1   (multiply by an opaque 1: IMAD, not SEL)
+            "@p mad.lo.u32 %1, %2, %6, 0;\n\t"    // w1 = w2
+            "@p mad.lo.u32 %3, %6, %7, %3;\n\t"   // nxt += row bytes
+            "@p ld.shared.u32 %2, [%3];\n\t"
+            "}"
+            : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(nxt)
+            : "r"(np), "r"(pos), "r"(T.one), "n"(NT * 4));
+#else
+        if ((np ^ pos) & 32u) {
             w0 = w1;
             w1 = w2;
             nxt += NT;
-#if defined(__CUDA_ARCH__)
-            // keeps this a predicated region (moves on the FMA pipe) instead of selects + address arithmetic on
-            // the INT pipe, which is what bounds this loop
-            asm volatile("");
-#endif
+            w2 = *nxt;
         }
-        // unconditional (re)load of the word after the window: issued a whole iteration before the slide that
-        // consumes it, so its latency never sits on the loop-carried path
-        w2 = *nxt;
+#endif
         pos = np;
     }
     uint32_t cnt = (((A - stage_addr) >> row_shift(NT)) << 2) | (A & 3u);
@@ -154,29 +179,42 @@ HD_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
 // Copy c symbols from the thread's staging column (word m at src[m * stride],
 // little-endian bytes) to byte offset D of the CTA's output tile: up to three
 // head bytes until the destination is word aligned, whole 32-bit words through
-// one funnel shift each, up to three tail bytes.  Reads at most one staging word
-// past the last one that holds symbols.
+// one funnel shift each, up to three tail bytes.  The words are fetched four at
+// a time BEFORE the stores of the batch (source and destination are both shared
+// memory, the compiler cannot reorder them itself), so that four loads are in
+// flight instead of one load -> shift -> store chain per word; head and tail are
+// predicated byte stores, not loops.  Reads at most three staging words past the
+// last one that holds symbols (rows of the next buffer: harmless).
 HD_HD void compact_to_tile(const uint32_t *src, uint32_t stride, uint32_t c, uint8_t *tile, uint32_t D) {
     uint32_t w = src[0];
     uint32_t head = (4u - (D & 3u)) & 3u;
     if (head > c) head = c;
-    for (uint32_t i = 0; i < head; ++i) tile[D + i] = (uint8_t)(w >> (8u * i));
-    uint32_t rem = c - head;
-    if (rem == 0) return;
+    if (head > 0u) tile[D] = (uint8_t)w;
+    if (head > 1u) tile[D + 1] = (uint8_t)(w >> 8);
+    if (head > 2u) tile[D + 2] = (uint8_t)(w >> 16);
+    const uint32_t rem = c - head;
+    const uint32_t nw = rem >> 2;
     uint32_t *dst = reinterpret_cast<uint32_t *>(tile + D + head);
     const uint32_t sh = 8u * head;
     const uint32_t *nx = src + stride;
-    while (rem >= 4u) {
-        const uint32_t n = *nx;
-        *dst++ = funnel_r(w, n, sh);
-        w = n;
-        nx += stride;
-        rem -= 4u;
+    for (uint32_t m = 0; m < nw; m += 4u) {
+        const uint32_t n0 = nx[0], n1 = nx[stride], n2 = nx[2u * stride], n3 = nx[3u * stride];
+        dst[0] = funnel_r(w, n0, sh);
+        if (m + 1u < nw) dst[1] = funnel_r(n0, n1, sh);
+        if (m + 2u < nw) dst[2] = funnel_r(n1, n2, sh);
+        if (m + 3u < nw) dst[3] = funnel_r(n2, n3, sh);
+        w = n3;
+        nx += 4u * stride;
+        dst += 4;
     }
-    if (rem) {
-        const uint32_t v = funnel_r(w, *nx, sh);
-        uint8_t *d8 = reinterpret_cast<uint8_t *>(dst);
-        for (uint32_t i = 0; i < rem; ++i) d8[i] = (uint8_t)(v >> (8u * i));
+    const uint32_t tail = rem & 3u;
+    if (tail) {
+        const uint32_t *lw = src + nw * stride;
+        const uint32_t v = funnel_r(lw[0], lw[stride], sh);
+        uint8_t *d8 = tile + D + head + 4u * nw;
+        d8[0] = (uint8_t)v;
+        if (tail > 1u) d8[1] = (uint8_t)(v >> 8);
+        if (tail > 2u) d8[2] = (uint8_t)(v >> 16);
     }
 }
 

@@ -258,13 +258,12 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             // (slot k % 3 was written by decode thread 0 during step k-1 and is not rewritten before step k+2)
             const uint64_t tile = s_tileid[k % 3u];
             if (tile >= p.n_tiles) break;
+            const bool tr = p.trace && blockIdx.x == kTraceCta && k < kTraceSteps && lane == 0;
             named_bar_sync(kBarFull + b, NT + 32);
-            // ticket of step k+2 (steps 0 and 1 got theirs in the prologue).  Issued here so that the atomic's
-            // round trip overlaps the look-back, but no earlier: a tile must not be claimed long before it is
-            // decoded, or every higher tile's look-back waits for it.
+            // ticket of step k+2 (steps 0 and 1 got theirs in the prologue).  Issued here, but no earlier: a tile must
+            // not be claimed long before it is decoded, or every higher tile's look-back waits for it.
             uint32_t ticket = 0;
             if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u);
-            const bool tr = p.trace && blockIdx.x == kTraceCta && k < kTraceSteps && lane == 0;
             if (tr) p.trace[k * 8 + 4] = gtime_ns();
             const uint32_t wt = lane < kNW ? s_wtot[b][lane] : 0u;
             uint32_t wi = wt;
@@ -275,10 +274,12 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             }
             if (lane < kNW) s_wtot[b][lane] = wi - wt;   // exclusive warp offsets
             const uint64_t agg = __shfl_sync(0xffffffffu, wi, kNW - 1);
-            // (the tile AGGREGATE was already published by the last decode warp to finish, so that it never waits
-            // behind this warp's look-back of the previous tile)
+            // (the tile AGGREGATE was already published by the last decode warp to finish; tile 0 published its PREFIX.)
+            // Looking back BEFORE the tile is full, while the predecessors are still being decoded, was measured and is
+            // slower: 148 scan warps polling the same few L2 lines delay the very publications they wait for.
             uint64_t excl = 0;
-            if (tile > 0) {
+            if (HD_WHATIF & 8) excl = tile * 40000ull;
+            if (tile > 0 && !(HD_WHATIF & 8)) {
                 uint32_t polls = 0;
                 excl = lookback_wide(p.tile_status, tile, lane, &polls);
                 if (tr) p.trace[k * 8 + 2] = polls;
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
     T.lut = s_lut;
     T.idx_shift = 32 - lm;
     T.lut_bits = lm;
+    T.one = lm != 0xffffffffu;   // 1 for every real table; ptxas cannot fold it
     T.len_tab = nullptr;
     T.lt = s_long;
     T.order = s_order;
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
                 col[(4 * SEGS + 0) * NT] = pf_la.x;
                 col[(4 * SEGS + 1) * NT] = pf_la.y;
                 if (tr) p.trace[k * 8 + 7] = gtime_ns();
-                cnt = decode_chunk<NT, LONG>(col, pf_entry, pf_stop, T, stage_abs + b * stage_buf_bytes + t * 4u, nullptr);
+                cnt = (HD_WHATIF & 4) ? 43u : decode_chunk<NT, LONG>(col, pf_entry, pf_stop, T, stage_abs + b * stage_buf_bytes + t * 4u, nullptr);
             }
             // ---------------- warp-wide inclusive scan of the counts ----------------
             incl = cnt;
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             while (ld_acquire_cta_u32(&s_t1_ready) == 0) __nanosleep(100);   // the scan warp's second ticket
         }
         if (valid) prefetch(s_tileid[(k + 1u) % 3u]);   // published with s_t1_ready / s_ready above
-        if (prev_valid) {
+        if (prev_valid && !(HD_WHATIF & 1)) {
             // ---------------- finish tile k-1: compact this WARP's symbols and flush them ----------------
             const uint32_t pb = b ^ 1u;
             const uint64_t base = s_base[pb];
@@ -447,8 +449,8 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             else if (my_off + c > p.n_symbols) c = (uint32_t)(p.n_symbols - my_off);
             const uint32_t A = (uint32_t)((reinterpret_cast<uintptr_t>(p.out) + base) & 15u);
             uint8_t *tile_buf = s_tile + (p.tile_buffers == 2u ? pb * p.tile_bytes : 0u);
-            if (c) compact_to_tile(reinterpret_cast<const uint32_t *>(s_stage + pb * stage_buf_bytes) + t, NT, c, tile_buf, A + excl_t);
-            fence_proxy_async_smem();
+            if (c && !(HD_WHATIF & 16)) compact_to_tile(reinterpret_cast<const uint32_t *>(s_stage + pb * stage_buf_bytes) + t, NT, c, tile_buf, A + excl_t);
+            if (!(HD_WHATIF & 128)) fence_proxy_async_smem();
             __syncwarp();
             // flush: the warp's span is contiguous in the tile and in the output, and both have the same 16-byte
             // phase -> one TMA bulk store for the aligned body, lanes 0-15 / 16-31 for head / tail bytes
@@ -461,12 +463,13 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             if (head > total) head = total;
             const uint32_t body = (total - head) & ~15u;
             const uint32_t tail = total - head - body;
-            if (lane == 0 && body) {
+            if (lane == 0 && body && !(HD_WHATIF & 32)) {
                 tma_bulk_store(gp + head, sp + head, body);
                 tma_bulk_commit();
                 store_pending = true;
             }
-            if (lane < 16) {
+            if (HD_WHATIF & 64) {
+            } else if (lane < 16) {
                 if (lane < head) gp[lane] = sp[lane];
             } else {
                 const uint32_t i = lane - 16;
@@ -618,7 +621,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
         const bool owner = active && (lane > 0 || ticket == 0);
         uint32_t words[2] = {0u, 0u};
         uint32_t entry = 0;
-        if (active) {
+        if (active && !(HD_WHATIF & 256)) {
             uint32_t i = kSyncChunkSegs * lane;   // unit index (within the staged tile) of the halo start
             uint32_t pos = 0;
             if (chunk == 0) {
@@ -653,7 +656,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
         const TileSegLoader tld{tile, q0};
         for (;;) {
             const uint32_t left = __shfl_up_sync(0xffffffffu, words[1] >> 28, 1);
-            const bool redo = active && lane > 0 && left != entry;
+            const bool redo = active && lane > 0 && left != entry && !(HD_WHATIF & 512);
             if (!__any_sync(0xffffffffu, redo)) break;
             if (redo) {
                 sync_repair_chunk<EXACT, LONG>(tld, chunk, left, L, words);

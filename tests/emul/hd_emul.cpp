@@ -27,6 +27,7 @@ void bind(HostTables &h) {
     h.T.lut = reinterpret_cast<const uint32_t *>(b);
     h.T.idx_shift = 32 - h.blob.lut_bits;
     h.T.lut_bits = h.blob.lut_bits;
+    h.T.one = 1;
     h.T.len_tab = b + h.blob.off_len;
     h.T.order = b + h.blob.off_order;
     h.T.lt = reinterpret_cast<const LongTables *>(b + h.blob.off_long);
