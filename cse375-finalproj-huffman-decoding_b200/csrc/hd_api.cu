@@ -7,6 +7,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -229,8 +230,11 @@ hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32
                          uint64_t n_segments, uint32_t first_bit, const hd_table *table, uint8_t *d_out,
                          uint64_t n_symbols, const Workspace &w, uint64_t *d_count, cudaStream_t s,
                          uint64_t n_units_readable = 0, const uint32_t *entry_word = nullptr,
-                         uint64_t *shard_info = nullptr, bool already_zeroed = false) {
+                         uint64_t *shard_info = nullptr, bool already_zeroed = false,
+                         const uint64_t *d_off_in = nullptr, uint64_t *d_off_out = nullptr) {
     DecodeParams p;
+    p.out_offset_in = d_off_in;
+    p.out_offset_out = d_off_out;
     p.units = d_units;
     p.n_units = n_units_readable > n_units ? n_units_readable : n_units;
     p.entry_word = entry_word;
@@ -623,20 +627,21 @@ static hd_status shard_args(const uint32_t *d_units, uint64_t n_units_halo, uint
 static hd_status shard_decode(const uint32_t *d_units, uint64_t n_units_halo, uint64_t n_units_shard,
                               uint64_t n_units_readable, uint32_t first_bit, const hd_table *table, uint8_t *d_out,
                               uint64_t out_cap, const Workspace &w, uint64_t *d_shard_info, cudaStream_t s,
-                              bool already_zeroed) {
+                              bool already_zeroed, const uint64_t *d_off_in = nullptr, uint64_t *d_off_out = nullptr) {
     const uint64_t halo_words = n_units_halo / (kSegmentUnits * 8);
     const uint32_t *gaps = w.gap_words + halo_words;
     return run_gap_decode(d_units + n_units_halo, n_units_shard, gaps, div_up(n_units_shard, kSegmentUnits), first_bit,
                           table, d_out, out_cap, w, nullptr, s, n_units_readable - n_units_halo,
-                          n_units_halo ? gaps - 1 : nullptr, d_shard_info, already_zeroed);
+                          n_units_halo ? gaps - 1 : nullptr, d_shard_info, already_zeroed, d_off_in, d_off_out);
 }
 
-// asynchronous half (see hd_decode_selfsync_enqueue)
-hd_status hd_decode_selfsync_shard_enqueue(const uint32_t *d_units, uint64_t n_units_halo, uint64_t n_units_shard,
-                                           uint64_t n_units_readable, uint32_t first_bit, const hd_table *table,
-                                           uint8_t *d_out, uint64_t out_cap, void *d_workspace,
-                                           size_t workspace_bytes, uint64_t *d_shard_info, uint32_t *h_unconverged,
-                                           void *stream) {
+// asynchronous half (see hd_decode_selfsync_enqueue); d_off_in / d_off_out chain the output position of consecutive
+// pieces on the device (host-buffer pipeline)
+static hd_status shard_enqueue_impl(const uint32_t *d_units, uint64_t n_units_halo, uint64_t n_units_shard,
+                                    uint64_t n_units_readable, uint32_t first_bit, const hd_table *table,
+                                    uint8_t *d_out, uint64_t out_cap, void *d_workspace, size_t workspace_bytes,
+                                    uint64_t *d_shard_info, uint32_t *h_unconverged, void *stream,
+                                    const uint64_t *d_off_in, uint64_t *d_off_out) {
     hd_status st = shard_args(d_units, n_units_halo, n_units_shard, n_units_readable, first_bit, table, d_out, out_cap,
                               d_workspace, workspace_bytes);
     if (st != HD_OK) return st;
@@ -651,10 +656,19 @@ hd_status hd_decode_selfsync_shard_enqueue(const uint32_t *d_units, uint64_t n_u
     st = run_sync(L, s);
     if (st != HD_OK) return st;
     st = shard_decode(d_units, n_units_halo, n_units_shard, n_units_readable, first_bit, table, d_out, out_cap, w,
-                      d_shard_info, s, true);
+                      d_shard_info, s, true, d_off_in, d_off_out);
     if (st != HD_OK) return st;
     if (L.p.n_chunks > 1) HD_CUDA(cudaMemcpyAsync(h_unconverged, w.changed, 4, cudaMemcpyDeviceToHost, s));
     return HD_OK;
+}
+
+hd_status hd_decode_selfsync_shard_enqueue(const uint32_t *d_units, uint64_t n_units_halo, uint64_t n_units_shard,
+                                           uint64_t n_units_readable, uint32_t first_bit, const hd_table *table,
+                                           uint8_t *d_out, uint64_t out_cap, void *d_workspace,
+                                           size_t workspace_bytes, uint64_t *d_shard_info, uint32_t *h_unconverged,
+                                           void *stream) {
+    return shard_enqueue_impl(d_units, n_units_halo, n_units_shard, n_units_readable, first_bit, table, d_out, out_cap,
+                              d_workspace, workspace_bytes, d_shard_info, h_unconverged, stream, nullptr, nullptr);
 }
 
 // synchronous half (see hd_decode_selfsync_finish)
@@ -885,8 +899,8 @@ hd_status hd_profile_read(float ms_out[HD_PROFILE_SLOTS]) {
 // Persistent device buffers + one stream: the per-call work is H2D, decode,
 // D2H -- the region gpuhd/src/demo.cc:170-197 ("Decompression time") and
 // decoder.cu:760-803 time, minus their per-call cudaMalloc.
-constexpr int kHostPieces = 16;          // upper bound of pipeline pieces per host-buffer decode
-constexpr uint64_t kHostPieceSegs = 1 << 20;   // 16 MiB of stream per piece (a multiple of every tile size); measured: 8 MiB pieces are slower (per-piece launch + sync overhead), PCIe in both directions at once is the floor
+constexpr int kHostPieces = 24;          // upper bound of pipeline pieces per host-buffer decode
+constexpr uint64_t kHostPieceSegs = 1 << 20;   // 16 MiB of stream per full piece (a multiple of every tile size); measured: 8 MiB pieces are slower (per-piece launch overhead), PCIe in both directions at once is the floor
 constexpr uint64_t kHostHaloSegs = 4096;  // left halo of a self-sync piece (64 KiB of stream)
 
 struct hd_host_decoder {
@@ -896,11 +910,11 @@ struct hd_host_decoder {
     size_t ws_bytes = 0;
     cudaStream_t stream = nullptr;                 // compute
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy engines: uploads / downloads overlap the decode
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_piece[kHostPieces] = {};         // "piece i is on the device"
-    cudaEvent_t ev_dec = nullptr;
-    uint64_t *d_info = nullptr;                     // {count, entry, exit} of the piece being decoded
+    cudaEvent_t ev_dec[kHostPieces] = {};           // "piece i is decoded and its info is in h_info"
+    uint64_t *d_info = nullptr;                     // per piece {count, entry, exit, output offset after the piece}
     uint64_t *h_info = nullptr;                     // pinned copy
+    uint32_t *h_flags = nullptr;                    // pinned, per piece: self-synchronisation did not converge blind
     hd_table *cached_table = nullptr;               // device tables of the last code seen (rebuilt only when it changes)
     std::vector<uint8_t> cached_key;
 };
@@ -913,10 +927,10 @@ void hd_host_decoder_destroy(hd_host_decoder *h) {
     if (h->d_ws) cudaFree(h->d_ws);
     if (h->d_info) cudaFree(h->d_info);
     if (h->h_info) cudaFreeHost(h->h_info);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
     hd_table_free(h->cached_table);
-    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     for (auto &e : h->ev_piece) if (e) cudaEventDestroy(e);
-    if (h->ev_dec) cudaEventDestroy(h->ev_dec);
+    for (auto &e : h->ev_dec) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
@@ -940,11 +954,11 @@ hd_status hd_host_decoder_create(int device, uint64_t max_units, uint64_t max_sy
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h->d_info), 64);
-    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&h->h_info), 64, cudaHostAllocDefault);
-    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h->d_info), kHostPieces * 32);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&h->h_info), kHostPieces * 32, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&h->h_flags), kHostPieces * 4, cudaHostAllocDefault);
     for (int i = 0; i < kHostPieces && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_piece[i], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_dec, cudaEventDisableTiming);
+    for (int i = 0; i < kHostPieces && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_dec[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         g_last_cuda = e;
         (void)cudaGetLastError();
@@ -955,51 +969,64 @@ hd_status hd_host_decoder_create(int device, uint64_t max_units, uint64_t max_sy
     return HD_OK;
 }
 
-// Host-buffer decode as a three-stage pipeline over pieces of the stream (16 MiB each): all uploads are queued on the
-// H2D stream up front, piece i is decoded on the compute stream as soon as it has arrived (a self-sync piece is a shard
-// with a 64 KiB left halo that is already on the device; a gap-array piece takes its entry offset from the gap array),
-// and its output is downloaded on the D2H stream while piece i+1 decodes.  PCIe runs in both directions at once, so
-// the wall time approaches max(H2D, D2H) instead of H2D + decode + D2H.
-// timing_ms = {time until the first piece is on the device, sum of the decode calls, time of the last download}.
-static hd_status host_decode_common(hd_host_decoder *h, const uint32_t *units, uint64_t n_units,
-                                    const uint8_t *gap_words, uint64_t n_segments, const hd_table *tab,
-                                    uint8_t *out, uint64_t n_symbols, float timing_ms[3]) {
-    if (n_units > h->max_units || n_symbols > h->max_symbols) return HD_ERR_INVALID;
-    HD_CUDA(cudaSetDevice(h->device));
+// Host-buffer decode as a three-stage pipeline over pieces of the stream: all uploads are queued on the H2D stream up
+// front; piece i is decoded on the compute stream as soon as it has arrived (a self-sync piece is a shard with a 64 KiB
+// left halo that is already on the device; a gap-array piece takes its entry offset from the gap array); its output is
+// downloaded on the D2H stream while the next pieces decode.  PCIe runs in both directions at once, so the wall time
+// approaches max(H2D, D2H) instead of H2D + decode + D2H (measured floor on this box for 100 MiB at redundancy 0.5:
+// 2.09 ms with both directions saturated, tools/pcie_probe.py).  Three things keep the downloads -- the longer
+// direction -- busy from early on and without gaps:
+//   * the first pieces are small (1/8, 1/4, 1/2 of a full 16 MiB piece), so the first download starts early;
+//   * the output position of piece i+1 is chained ON THE DEVICE (K4 reads the running offset the previous launch
+//     left behind), so pieces are enqueued two ahead and the compute stream never waits for the host;
+//   * the host only waits for "piece i decoded" events to learn {count, entry, exit} and queue the download.
+// A self-sync piece whose halo did not synchronise it, or whose blind synchronisation did not converge (codes that do
+// not self-synchronise), sends the rest of the stream down the serial path: one piece at a time, exact entry offsets.
+// timing_ms = {time until the first piece is on the device, from then until the last piece is decoded (uploads and
+// downloads overlap it), time of the remaining downloads}.
+struct HostPlan {
+    int n_pieces;
+    uint64_t seg[kHostPieces + 1];   // piece i = segments [seg[i], seg[i+1])
+};
+
+static HostPlan host_plan(uint64_t n_seg) {
+    HostPlan P;
+    static const uint64_t tuned = [] {   // developer knob: HD_HOST_PIECE_LOG2 = log2(segments per full piece)
+        const char *e = std::getenv("HD_HOST_PIECE_LOG2");
+        const int v = e ? std::atoi(e) : 0;
+        return v >= 13 && v <= 24 ? (uint64_t)1 << v : kHostPieceSegs;
+    }();
+    uint64_t base = tuned;
+    if (n_seg > base * (kHostPieces - 3)) base = align_up(div_up(n_seg, kHostPieces - 3), 8192);
+    // ramp up (1/8, 1/4, 1/2 of a full piece) so that the first download starts early, then full pieces.  A ramp down
+    // at the end (short last download) was measured and is no faster: with the uploads queued up front the two PCIe
+    // directions are both busy until the end either way, and more pieces cost more (tools/pcie_probe.py: dependent
+    // piecewise copies alone, without any decode, take 2.64 ms for this workload; the whole call takes 2.63 ms).
+    const uint64_t ramp[3] = {base / 8, base / 4, base / 2};
+    int n = 0;
+    uint64_t s = 0;
+    P.seg[0] = 0;
+    while (s < n_seg) {
+        uint64_t take = n < 3 ? ramp[n] : base;
+        if (n_seg - s < take + ramp[0]) take = n_seg - s;   // no sliver at the end
+        s += take;
+        P.seg[++n] = s;
+    }
+    P.n_pieces = n;
+    return P;
+}
+
+// serial tail of the pipeline (and the whole of it for codes that do not self-synchronise): pieces i0.. one at a time
+static hd_status host_decode_serial(hd_host_decoder *h, const HostPlan &P, int i0, uint64_t offset, uint64_t prev_exit,
+                                    uint64_t n_units, const uint8_t *gap_words, const hd_table *tab, uint8_t *out,
+                                    uint64_t n_symbols) {
     uint32_t *d_units = reinterpret_cast<uint32_t *>(h->d_units);
     uint32_t *d_gaps = reinterpret_cast<uint32_t *>(h->d_gaps);
-    const uint64_t n_seg = div_up(n_units, kSegmentUnits);
-    uint64_t piece_segs = kHostPieceSegs;
-    if (div_up(n_seg, piece_segs) > (uint64_t)kHostPieces) piece_segs = align_up(div_up(n_seg, kHostPieces), 1024);
-    const int n_pieces = (int)div_up(n_seg, piece_segs);
-    const auto t0 = std::chrono::steady_clock::now();
-
-    // ---- stage 1: every upload, one event per piece (a piece also brings the next piece's first unit along: the
-    // last codeword of a piece may end there; re-uploading those 16 bytes is harmless)
-    if (gap_words) {
-        HD_CUDA(cudaMemcpyAsync(d_gaps, gap_words, div_up(n_segments, 8) * 4, cudaMemcpyHostToDevice, h->s_h2d));
-    }
-    for (int i = 0; i < n_pieces; ++i) {
-        const uint64_t u0 = (uint64_t)i * piece_segs * 4;
-        const uint64_t u1 = std::min<uint64_t>(n_units, ((uint64_t)i + 1) * piece_segs * 4 + 4);
-        HD_CUDA(cudaMemcpyAsync(d_units + u0, units + u0, (u1 - u0) * 4, cudaMemcpyHostToDevice, h->s_h2d));
-        HD_CUDA(cudaEventRecord(h->ev_piece[i], h->s_h2d));
-    }
-
-    // ---- stages 2+3: decode piece i, then queue its download and go on with piece i+1
-    uint64_t offset = 0;            // symbols decoded so far = where the next piece's output goes
-    uint64_t prev_exit = 0;
-    double first_ms = 0, dec_ms = 0;
-    for (int i = 0; i < n_pieces && offset < n_symbols; ++i) {
-        const uint64_t s0 = (uint64_t)i * piece_segs, s1 = std::min<uint64_t>(n_seg, s0 + piece_segs);
+    for (int i = i0; i < P.n_pieces && offset < n_symbols; ++i) {
+        const uint64_t s0 = P.seg[i], s1 = P.seg[i + 1];
         const uint64_t shard_units = std::min<uint64_t>(n_units, s1 * 4) - s0 * 4;
         const uint64_t readable_end = std::min<uint64_t>(n_units, s1 * 4 + 4);
         HD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_piece[i], 0));
-        if (i == 0) {
-            HD_CUDA(cudaEventSynchronize(h->ev_piece[0]));
-            first_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        }
-        const auto td = std::chrono::steady_clock::now();
         hd_status st;
         if (gap_words) {
             uint32_t first_bit = 0;
@@ -1030,20 +1057,111 @@ static hd_status host_decode_common(hd_host_decoder *h, const uint32_t *units, u
             HD_CUDA(cudaMemcpyAsync(h->h_info, h->d_info, 24, cudaMemcpyDeviceToHost, h->stream));
             HD_CUDA(cudaStreamSynchronize(h->stream));
         }
-        dec_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - td).count();
-        const uint64_t count = gap_words ? h->h_info[0] : h->h_info[0];
+        const uint64_t count = h->h_info[0];
         prev_exit = h->h_info[2];
-        // the compute stream is idle here (synchronised above): the download may start right away on its own stream
         HD_CUDA(cudaMemcpyAsync(out + offset, h->d_out + offset, count, cudaMemcpyDeviceToHost, h->s_d2h));
         offset += count;
+    }
+    HD_CUDA(cudaStreamSynchronize(h->s_d2h));
+    HD_CUDA(cudaStreamSynchronize(h->s_h2d));
+    return offset < n_symbols ? HD_ERR_FORMAT : HD_OK;   // FORMAT: the stream holds fewer codewords than asked for
+}
+
+static hd_status host_decode_common(hd_host_decoder *h, const uint32_t *units, uint64_t n_units,
+                                    const uint8_t *gap_words, uint64_t n_segments, const hd_table *tab,
+                                    uint8_t *out, uint64_t n_symbols, float timing_ms[3]) {
+    if (n_units > h->max_units || n_symbols > h->max_symbols) return HD_ERR_INVALID;
+    HD_CUDA(cudaSetDevice(h->device));
+    uint32_t *d_units = reinterpret_cast<uint32_t *>(h->d_units);
+    uint32_t *d_gaps = reinterpret_cast<uint32_t *>(h->d_gaps);
+    const uint64_t n_seg = div_up(n_units, kSegmentUnits);
+    const HostPlan P = host_plan(n_seg);
+    const auto t0 = std::chrono::steady_clock::now();
+
+    // ---- stage 1: every upload, one event per piece (a piece also brings the next piece's first unit along: the
+    // last codeword of a piece may end there; re-uploading those 16 bytes is harmless)
+    if (gap_words) {
+        HD_CUDA(cudaMemcpyAsync(d_gaps, gap_words, div_up(n_segments, 8) * 4, cudaMemcpyHostToDevice, h->s_h2d));
+    }
+    for (int i = 0; i < P.n_pieces; ++i) {
+        const uint64_t u0 = P.seg[i] * 4;
+        const uint64_t u1 = std::min<uint64_t>(n_units, P.seg[i + 1] * 4 + 4);
+        HD_CUDA(cudaMemcpyAsync(d_units + u0, units + u0, (u1 - u0) * 4, cudaMemcpyHostToDevice, h->s_h2d));
+        HD_CUDA(cudaEventRecord(h->ev_piece[i], h->s_h2d));
+    }
+
+    // ---- stage 2: decode piece i into d_out at the offset the previous piece left on the device
+    auto enqueue_piece = [&](int i) -> hd_status {
+        const uint64_t s0 = P.seg[i], s1 = P.seg[i + 1];
+        const uint64_t shard_units = std::min<uint64_t>(n_units, s1 * 4) - s0 * 4;
+        const uint64_t readable_end = std::min<uint64_t>(n_units, s1 * 4 + 4);
+        uint64_t *info = h->d_info + 4 * i;
+        const uint64_t *off_in = i ? h->d_info + 4 * (i - 1) + 3 : nullptr;
+        HD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_piece[i], 0));
+        hd_status st;
+        if (gap_words) {
+            uint32_t first_bit = 0;
+            if (s0) {
+                const uint64_t j = s0 - 1;
+                uint32_t w;
+                std::memcpy(&w, gap_words + (j >> 3) * 4, 4);
+                first_bit = (w >> (4u * (uint32_t)(j & 7))) & 15u;
+            }
+            const uint64_t piece_units = readable_end - s0 * 4;
+            Workspace w = carve(h->d_ws, piece_units, false);
+            st = run_gap_decode(d_units + s0 * 4, piece_units, d_gaps + s0 / 8, s1 - s0, first_bit, tab, h->d_out,
+                                n_symbols, w, info, h->stream, 0, nullptr, nullptr, false, off_in, info + 3);
+            h->h_flags[i] = 0;
+        } else {
+            const uint64_t halo = std::min<uint64_t>(kHostHaloSegs, s0);
+            st = shard_enqueue_impl(d_units + (s0 - halo) * 4, halo * 4, shard_units, readable_end - (s0 - halo) * 4, 0,
+                                    tab, h->d_out, n_symbols, h->d_ws, h->ws_bytes, info, h->h_flags + i, h->stream,
+                                    off_in, info + 3);
+        }
+        if (st != HD_OK) return st;
+        HD_CUDA(cudaMemcpyAsync(h->h_info + 4 * i, info, 32, cudaMemcpyDeviceToHost, h->stream));
+        HD_CUDA(cudaEventRecord(h->ev_dec[i], h->stream));
+        return HD_OK;
+    };
+    int enq = 0;
+    for (; enq < P.n_pieces && enq < 2; ++enq) {
+        hd_status st = enqueue_piece(enq);
+        if (st != HD_OK) return st;
+    }
+    HD_CUDA(cudaEventSynchronize(h->ev_piece[0]));
+    const auto t1 = std::chrono::steady_clock::now();
+
+    // ---- stage 3: as pieces finish, queue their downloads and keep two pieces enqueued ahead
+    uint64_t offset = 0, prev_exit = 0;
+    for (int i = 0; i < P.n_pieces; ++i) {
+        HD_CUDA(cudaEventSynchronize(h->ev_dec[i]));
+        const uint64_t *info = h->h_info + 4 * i;
+        if (!gap_words && (h->h_flags[i] != 0 || (i > 0 && info[1] != prev_exit))) {
+            HD_CUDA(cudaStreamSynchronize(h->stream));   // pieces enqueued ahead decoded to a wrong position: drop them
+            const hd_status st = host_decode_serial(h, P, i, offset, prev_exit, n_units, gap_words, tab, out, n_symbols);
+            if (timing_ms) {
+                timing_ms[0] = (float)std::chrono::duration<double, std::milli>(t1 - t0).count();
+                timing_ms[1] = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+                timing_ms[2] = 0.f;
+            }
+            return st;
+        }
+        const uint64_t count = info[0];
+        prev_exit = info[2];
+        if (count) HD_CUDA(cudaMemcpyAsync(out + offset, h->d_out + offset, count, cudaMemcpyDeviceToHost, h->s_d2h));
+        offset += count;
+        if (enq < P.n_pieces) {
+            hd_status st = enqueue_piece(enq++);
+            if (st != HD_OK) return st;
+        }
     }
     const auto t2 = std::chrono::steady_clock::now();
     HD_CUDA(cudaStreamSynchronize(h->s_d2h));
     HD_CUDA(cudaStreamSynchronize(h->s_h2d));
     if (offset < n_symbols) return HD_ERR_FORMAT;   // the stream holds fewer codewords than asked for
     if (timing_ms) {
-        timing_ms[0] = (float)first_ms;
-        timing_ms[1] = (float)dec_ms;
+        timing_ms[0] = (float)std::chrono::duration<double, std::milli>(t1 - t0).count();
+        timing_ms[1] = (float)std::chrono::duration<double, std::milli>(t2 - t1).count();
         timing_ms[2] = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count();
     }
     return HD_OK;

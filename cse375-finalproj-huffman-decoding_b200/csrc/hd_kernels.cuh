@@ -82,6 +82,9 @@ struct DecodeParams {
     TableDev table;
     uint8_t *out;
     uint64_t n_symbols;
+    const uint64_t *out_offset_in;   // optional: decode to out + *out_offset_in (output capacity n_symbols counts from `out`);
+    uint64_t *out_offset_out;        // optional: receives *out_offset_in + symbols written -- chains the pieces of a
+                                     // pipelined host-buffer decode on the device, without a host round trip per piece
     uint64_t *tile_status;       // n_tiles words, zeroed before launch
     uint32_t *tile_counter;      // zeroed before launch
     uint64_t n_tiles;
@@ -204,6 +207,10 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
     const uint32_t lane = t & 31, warp = t >> 5;
     const uint32_t lm = p.table.lut_bits;
     const uint32_t lut_bytes = 4u << lm;
+    // where this launch's output starts (chained pieces: written by the previous launch on the stream)
+    const uint64_t out_off = p.out_offset_in ? *p.out_offset_in : 0ull;
+    uint8_t *const out = p.out + out_off;
+    const uint64_t n_symbols = p.n_symbols > out_off ? p.n_symbols - out_off : 0ull;
 
     uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem);
     uint8_t *s_order = smem + lut_bytes;
@@ -290,8 +297,9 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
                 s_total[b] = (uint32_t)agg;
                 if (tile + 1 == p.n_tiles) {
                     uint64_t tot = excl + agg;
-                    tot = tot < p.n_symbols ? tot : p.n_symbols;
+                    tot = tot < n_symbols ? tot : n_symbols;
                     if (p.count_out) *p.count_out = tot;
+                    if (p.out_offset_out) *p.out_offset_out = out_off + tot;
                     if (p.shard_info) {
                         p.shard_info[0] = tot;
                         p.shard_info[1] = p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit;
@@ -445,9 +453,9 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             // out_pos < next_out_pos, cuhd_gpu_decoder.cu:101-105)
             const uint64_t my_off = base + excl_t;
             uint32_t c = prev_cnt;
-            if (my_off >= p.n_symbols) c = 0;
-            else if (my_off + c > p.n_symbols) c = (uint32_t)(p.n_symbols - my_off);
-            const uint32_t A = (uint32_t)((reinterpret_cast<uintptr_t>(p.out) + base) & 15u);
+            if (my_off >= n_symbols) c = 0;
+            else if (my_off + c > n_symbols) c = (uint32_t)(n_symbols - my_off);
+            const uint32_t A = (uint32_t)((reinterpret_cast<uintptr_t>(out) + base) & 15u);
             uint8_t *tile_buf = s_tile + (p.tile_buffers == 2u ? pb * p.tile_bytes : 0u);
             if (c && !(HD_WHATIF & 16)) compact_to_tile(reinterpret_cast<const uint32_t *>(s_stage + pb * stage_buf_bytes) + t, NT, c, tile_buf, A + excl_t);
             if (!(HD_WHATIF & 128)) fence_proxy_async_smem();
@@ -455,10 +463,10 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             // flush: the warp's span is contiguous in the tile and in the output, and both have the same 16-byte
             // phase -> one TMA bulk store for the aligned body, lanes 0-15 / 16-31 for head / tail bytes
             const uint64_t wbase = base + woff;
-            uint64_t lim = wbase >= p.n_symbols ? 0 : p.n_symbols - wbase;
+            uint64_t lim = wbase >= n_symbols ? 0 : n_symbols - wbase;
             const uint32_t total = wtot < lim ? wtot : (uint32_t)lim;
             const uint8_t *sp = tile_buf + A + woff;
-            uint8_t *gp = p.out + wbase;
+            uint8_t *gp = out + wbase;
             uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(gp) & 15u)) & 15u;
             if (head > total) head = total;
             const uint32_t body = (total - head) & ~15u;

@@ -243,13 +243,15 @@ hd_status hd_huff_decode_host(const void *file, size_t size, uint8_t *out,
  * call = H2D + decode + D2H, the region the reference demos time
  * (gpuhd/src/demo.cc:170-197 "Decompression time"; decoder.cu:760-803
  * "HtoD,dec,DtoH"), without their per-call cudaMalloc.  The call is a
- * three-stage pipeline over 16 MiB pieces of the stream: uploads, decodes and
- * downloads of different pieces overlap (PCIe in both directions at once), so
- * the wall time approaches max(H2D, D2H).  Host pointers should be pinned for
- * full PCIe rate and real overlap (the reference pins too,
- * decoder/src/huff.cpp:44,88).  timing_ms (may be NULL) = host milliseconds
- * {until the first piece is on the device, spent in the decode calls, waiting
- * for the last download}. */
+ * three-stage pipeline over pieces of the stream (2, 4, 8, then 16 MiB each):
+ * uploads, decodes and downloads of different pieces overlap (PCIe in both
+ * directions at once), so the wall time approaches max(H2D, D2H); the output
+ * position of consecutive pieces is chained on the device, the host only
+ * queues the downloads.  Host pointers should be pinned for full PCIe rate and
+ * real overlap (the reference pins too, decoder/src/huff.cpp:44,88).
+ * timing_ms (may be NULL) = host milliseconds {until the first piece is on the
+ * device, from then until the last piece is decoded, waiting for the
+ * remaining downloads}. */
 typedef struct hd_host_decoder hd_host_decoder;
 hd_status hd_host_decoder_create(int device, uint64_t max_units,
                                  uint64_t max_symbols, hd_host_decoder **out);
