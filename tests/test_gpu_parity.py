@@ -536,3 +536,38 @@ def test_mailbox_single_rank_roundtrip(hd, torch_cuda):
     assert L.hd_mailbox_timed_out(h) == 0
     assert L.hd_mailbox_publish(h, C.c_void_p(info.data_ptr()), 0, sp) != 0     # seq 0 is reserved
     L.hd_mailbox_destroy(h)
+
+
+def test_beyond_4_gib(hd, torch_cuda):
+    """4.5 GiB round trip entirely on the device (device encoder -> both decoders -> compare): 64-bit sizes end to end.
+    The reference's formats and kernels stop at 4 GiB / 2 GiB (32-bit sizes); the property checked is the
+    size-independent one, decode(encode(x)) == x."""
+    torch = torch_cuda
+    free, _ = torch.cuda.mem_get_info()
+    if free < (24 << 30):
+        pytest.skip("needs 24 GiB of free device memory")
+    n = int(4.5 * (1 << 30)) + 12345
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    data = torch.empty(n, dtype=torch.uint8, device="cuda")
+    step = 1 << 28
+    for o in range(0, n, step):      # half of the mass on 4 symbols (the generate.cpp shape), the rest uniform
+        m = min(step, n - o)
+        u = torch.randint(0, 256, (m,), dtype=torch.int16, device="cuda", generator=g)
+        hot = torch.randint(0, 2, (m,), dtype=torch.int16, device="cuda", generator=g)
+        data[o:o + m] = torch.where(hot == 1, u & 3, u).to(torch.uint8)
+        del u, hot
+    for max_len, selfsync in ((16, False), (11, True)):
+        pairs, d_units, d_gaps, bits = hd.encode_device(data, max_len, pad_unit=selfsync)
+        assert bits > (1 << 34)
+        tab = hd.Codetable(flat_lut=hd.flat_lut(pairs, 11)) if selfsync else hd.Codetable(pairs=pairs)
+        dec = hd.Decoder(d_units.numel(), selfsync=selfsync)
+        out = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        if selfsync:
+            dec.decode_selfsync(d_units, tab, n, out=out)
+        else:
+            dec.decode_gap(d_units, d_gaps, tab, n, out=out)
+        torch.cuda.synchronize()
+        assert bool(torch.equal(out, data))
+        tab.close()
+        del out, dec, d_units, d_gaps
