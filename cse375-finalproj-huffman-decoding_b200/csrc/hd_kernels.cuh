@@ -56,6 +56,25 @@ __device__ __forceinline__ void tma_bulk_wait0() { asm volatile("cp.async.bulk.w
 // make generic-proxy smem writes visible to the async (TMA) proxy
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// shared-memory transaction barrier used as a one-producer flag: waiters are suspended by the hardware instead of
+// spinning on a load (a spinning warp takes issue slots from the decode warps of its scheduler)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(a), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
 // ------------------------------------------------------------ kernel params
 constexpr uint64_t kFlagAggregate = 1ull << 62;   // tile aggregate published
 constexpr uint64_t kFlagPrefix = 2ull << 62;      // inclusive prefix published
@@ -230,7 +249,10 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
     __shared__ unsigned long long s_base[2];
     __shared__ uint32_t s_total[2];
     __shared__ uint32_t s_sum[2], s_arrived[2];   // tile total / number of warps that added theirs
-    __shared__ uint32_t s_ready[2];               // s_ready[b] = k+1 once the prefix of step k (buffer b) is in s_base[b]
+    // s_ready[b] completes its n-th phase once the prefix of step k = b + 2n is in s_base[b].  Parity waits are safe:
+    // the scan warp cannot finish step k+2 (the next phase of the same barrier) before every decode warp has arrived
+    // at FULL of step k+1, i.e. has long left its wait for step k.
+    __shared__ __align__(8) unsigned long long s_ready[2];
     __shared__ uint32_t s_t1_ready;               // the tile of step 1 is in s_tileid[1]
 
     // Tickets: every tile id comes from the atomic counter, so tiles are only ever claimed by CTAs that are running
@@ -239,7 +261,7 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
     // look-back depends only on tiles that are decoded in the same step by the other CTAs, not on second tiles.
     if (t == NT) s_tileid[0] = atomicAdd(p.tile_counter, 1u);
     // ---- stage the tables once per CTA (persistent) ----
-    if (t < 2) { s_sum[t] = 0; s_arrived[t] = 0; s_ready[t] = 0; }
+    if (t < 2) { s_sum[t] = 0; s_arrived[t] = 0; mbar_init(&s_ready[t], 1u); }
     if (t == 0) s_t1_ready = 0;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.table.blob);
@@ -312,7 +334,7 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             if (lane == 0) s_tileid[(k + 2u) % 3u] = ticket;
             __syncwarp();
             __threadfence_block();
-            if (lane == 0) st_release_cta_u32(&s_ready[b], k + 1u);
+            if (lane == 0) mbar_arrive(&s_ready[b]);
         }
         return;
     }
@@ -436,7 +458,7 @@ __global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const Decod
             }
             // wait for the scan warp's prefix of tile k-1 (computed while we decoded tile k): a flag, not a
             // barrier, so that with two output tiles no decode warp ever waits for another decode warp
-            while (ld_acquire_cta_u32(&s_ready[b ^ 1u]) < k) __nanosleep(200);
+            mbar_wait(&s_ready[b ^ 1u], ((k - 1u) >> 1) & 1u);
         }
         if (k == 0) {
             while (ld_acquire_cta_u32(&s_t1_ready) == 0) __nanosleep(100);   // the scan warp's second ticket
