@@ -5,9 +5,10 @@
 //        Replaces gpu_dec_l1_l2 (Huffman_coding_Gap_arrays/decoder/src/
 //        decoder.cu:454-730) and phases 3+4 of CUHD (gpuhd/src/
 //        cuhd_gpu_decoder.cu:329-420 + thrust scan :498-505).
-//   K1a hd_sync_chunks_kernel  : speculative subsequence synchronisation inside
-//        a block to a fixed point (replaces phase 1, cuhd_gpu_decoder.cu:145-233)
-//   K1b hd_sync_seams_kernel   : block-seam synchronisation to a fixed point
+//   K1a hd_sync_parse_kernel   : speculative subsequence synchronisation: every
+//        thread parses a halo + its chunk, seams are repaired inside the warp
+//        (replaces phase 1, cuhd_gpu_decoder.cu:145-233)
+//   K1b hd_sync_walk_kernel    : seams between warp tiles, walked to the merge
 //        (replaces phase 2 + host loop, cuhd_gpu_decoder.cu:235-327, 461-495)
 //
 // Integer/byte work only: no tensor cores.  See DESIGN.md for the data layout
@@ -147,15 +148,16 @@ struct SyncParams {
 //                           wait READY[(k-1)&1]  (prefix of tile k-1, long done)
 //                           compact staging[(k-1)&1] -> output tile, flush it
 //                           (one TMA bulk store, SASS UBLKCP, + scalar head/tail)
-//   scan warp, step k:      take the ticket for step k+2; wait FULL[k&1]; scan
-//                           the warp totals; publish the tile aggregate; look
-//                           back over predecessors' aggregates/prefixes (64-bit
-//                           flagged words, ld/st.relaxed.gpu); publish the
-//                           inclusive prefix; arrive READY[k&1]
+//   scan warp, step k:      wait FULL[k&1]; take the ticket for step k+2; scan
+//                           the warp totals (the tile aggregate was published
+//                           by the last decode warp to finish); look back over
+//                           the predecessors' aggregates/prefixes (64-bit
+//                           flagged words, ld.relaxed.gpu / red.max); publish
+//                           the inclusive prefix; arrive READY[k&1]
 //
-// FULL/READY are named barriers (bar.arrive / bar.sync): the only CTA-wide
-// synchronisation per tile besides one barrier among the decode warps between
-// compaction and flush.
+// FULL is a named barrier (decode warps bar.arrive, the scan warp bar.sync),
+// READY an mbarrier the decode warps wait on: no decode warp ever waits for
+// another decode warp (with two output tiles), only for the scan warp.
 // =========================================================================
 __device__ __forceinline__ uint32_t gap_nibble(const uint32_t *gap_words, uint64_t j) {
     return (__ldg(gap_words + (j >> 3)) >> (4u * (uint32_t)(j & 7))) & 15u;
