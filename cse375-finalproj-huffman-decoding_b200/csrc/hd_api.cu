@@ -73,6 +73,8 @@ struct Workspace {
     uint64_t *tile_status;
     uint32_t *changed;       // 8 counters
     uint64_t *count;
+    uint32_t *sync_exit;     // self-sync: one published exit word per K1a warp tile (zeroed per call)
+    size_t sync_zero_bytes;  // self-sync: bytes from `changed` on that must be zeroed per call
     uint32_t *gap_words;
     uint8_t *blk_entry;      // per sync chunk: entry offset its landings were parsed from
     size_t zero_bytes;       // prefix of the workspace that must be zeroed per K4 launch
@@ -86,6 +88,7 @@ size_t ws_bytes(uint64_t n_units, bool selfsync) {
     size_t b = kCtrlBytes + align_up(n_tiles * 8 * kStatusStride, 64) + kCtrlBytes;
     if (selfsync) {
         const uint64_t n_chunks = std::max<uint64_t>(1, div_up(n_seg, kSyncChunkSegs));
+        b += align_up((div_up(n_chunks, kSyncTileChunks) + 1) * 4, 64);
         b += align_up(n_chunks * (kSyncChunkSegs / 8) * 4, 64) + align_up(n_chunks, 64);
     }
     return b;
@@ -104,10 +107,15 @@ Workspace carve(void *ws, uint64_t n_units, bool selfsync) {
     w.count = reinterpret_cast<uint64_t *>(b + 48);
     w.gap_words = nullptr;
     w.blk_entry = nullptr;
+    w.sync_exit = nullptr;
+    w.sync_zero_bytes = kCtrlBytes;
     if (selfsync) {
         const uint64_t n_chunks = std::max<uint64_t>(1, div_up(n_seg, kSyncChunkSegs));
-        w.gap_words = reinterpret_cast<uint32_t *>(b + kCtrlBytes);
-        w.blk_entry = b + kCtrlBytes + align_up(n_chunks * (kSyncChunkSegs / 8) * 4, 64);
+        const size_t exit_bytes = align_up((div_up(n_chunks, kSyncTileChunks) + 1) * 4, 64);
+        w.sync_exit = reinterpret_cast<uint32_t *>(b + kCtrlBytes);
+        w.sync_zero_bytes = kCtrlBytes + exit_bytes;
+        w.gap_words = reinterpret_cast<uint32_t *>(b + kCtrlBytes + exit_bytes);
+        w.blk_entry = b + kCtrlBytes + exit_bytes + align_up(n_chunks * (kSyncChunkSegs / 8) * 4, 64);
     }
     return w;
 }
@@ -279,7 +287,7 @@ struct SyncLaunch {
 
 SyncLaunch make_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit, const hd_table *table,
                             uint32_t *d_gap_words, uint8_t *d_cur_entry, uint32_t *d_ctrl, uint64_t n_units_readable,
-                            bool exact) {
+                            bool exact, uint32_t *d_sync_exit) {
     SyncLaunch L;
     SyncParams &p = L.p;
     p.units = d_units;
@@ -287,6 +295,7 @@ SyncLaunch make_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_b
     p.n_segments = div_up(n_units, kSegmentUnits);
     p.n_chunks = div_up(p.n_segments, kSyncChunkSegs);
     p.n_tiles = std::max<uint64_t>(1, div_up(p.n_chunks - 1, kSyncTileChunks));   // tile t owns chunks 31t+1 .. 31t+31 (+ chunk 0)
+    p.tile_exit = d_sync_exit;
     p.first_bit = first_bit;
     p.table = table_dev(table);
     p.gap_words = d_gap_words;
@@ -331,25 +340,19 @@ hd_status launch_sync_walk(const SyncLaunch &L, uint32_t *changed, cudaStream_t 
     ((L).exact ? ((L).lng ? fn<true, true>((L), __VA_ARGS__) : fn<true, false>((L), __VA_ARGS__))   \
                : ((L).lng ? fn<false, true>((L), __VA_ARGS__) : fn<false, false>((L), __VA_ARGS__)))
 
-// K1a + ONE blind K1b round.  changed[0] counts the groups whose EXIT moved in that round; if it is zero every seam was
-// checked against an exit that never changed afterwards, i.e. the fixed point is reached (a second round could not
-// change anything).  d_ctrl must be zeroed (kCtrlBytes) before.
+// K1a alone: every warp tile publishes the offset at which its parse leaves it, and its warp later checks the tile's
+// first seam against the exit the predecessor published (one tile later, when that exit has long been there: no wait
+// and no second launch).  changed[0] counts the tiles whose exit moved AFTER they had published it (a seam repair that
+// ran through the whole tile) and the waits that timed out: zero means every seam was checked against an exit that
+// never changed afterwards, i.e. the fixed point is reached.  d_ctrl + the published exits must be zeroed
+// (Workspace::sync_zero_bytes) before.
 hd_status run_sync(const SyncLaunch &L, cudaStream_t s) {
-    {
-        ProfScope prof(HD_PROFILE_SYNC_CHUNKS, s);
-        hd_status st = HD_SYNC_DISPATCH(launch_sync_parse, L, s);
-        if (st != HD_OK) return st;
-    }
-    if (L.p.n_chunks > 1) {
-        ProfScope prof(HD_PROFILE_SYNC_SEAMS, s);
-        hd_status st = HD_SYNC_DISPATCH(launch_sync_walk, L, L.p.changed, s);
-        if (st != HD_OK) return st;
-    }
-    return HD_OK;
+    ProfScope prof(HD_PROFILE_SYNC_CHUNKS, s);
+    return HD_SYNC_DISPATCH(launch_sync_parse, L, s);
 }
 
-// further rounds until no chunk exit changes (host loop of the reference: cuhd_gpu_decoder.cu:461-495); only
-// reached for codes that fail to synchronise inside a whole 2048-bit chunk.
+// K1b rounds until no tile exit changes (host loop of the reference: cuhd_gpu_decoder.cu:461-495); only reached for
+// codes that fail to synchronise inside a whole warp tile (64 Kbit).
 hd_status finish_sync(const SyncLaunch &L, cudaStream_t s, bool *extra_rounds) {
     *extra_rounds = false;
     if (L.p.n_chunks <= 1) return HD_OK;
@@ -362,6 +365,7 @@ hd_status finish_sync(const SyncLaunch &L, cudaStream_t s, bool *extra_rounds) {
     const uint64_t max_rounds = div_up(L.p.n_chunks, kSyncWalkChunks) + 3;
     for (uint64_t round = 0; round <= max_rounds; ++round) {
         HD_CUDA(cudaMemsetAsync(changed, 0, 4, s));
+        ProfScope prof(HD_PROFILE_SYNC_SEAMS, s);
         hd_status st = HD_SYNC_DISPATCH(launch_sync_walk, L, changed, s);
         if (st != HD_OK) return st;
         HD_CUDA(cudaMemcpyAsync(&h_changed, changed, 4, cudaMemcpyDeviceToHost, s));
@@ -526,9 +530,9 @@ hd_status hd_selfsync_gap_array(const uint32_t *d_units, uint64_t n_units, uint3
     if (workspace_bytes < ws_bytes(n_units, true)) return HD_ERR_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Workspace w = carve(d_workspace, n_units, true);
-    HD_CUDA(cudaMemsetAsync(w.changed, 0, kCtrlBytes, s));
+    HD_CUDA(cudaMemsetAsync(w.changed, 0, w.sync_zero_bytes, s));
     // exact landings: this entry returns a gap array in the .huff sense (first codeword of every segment)
-    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, true);
+    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, true, w.sync_exit);
     st = run_sync(L, s);
     if (st != HD_OK) return st;
     bool extra = false;
@@ -559,8 +563,8 @@ hd_status hd_decode_selfsync_enqueue(const uint32_t *d_units, uint64_t n_units, 
     // K1a + K1b, then K4 speculatively; the convergence flag is read once at the end (the reference reads a flag
     // array after every phase-2 launch, cuhd_gpu_decoder.cu:461-495).  One memset covers K4's ticket counter and
     // tile statuses and, right behind them, K1's control block.
-    HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes + kCtrlBytes, s));
-    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, false);
+    HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes + w.sync_zero_bytes, s));
+    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, false, w.sync_exit);
     st = run_sync(L, s);
     if (st != HD_OK) return st;
     st = run_gap_decode(d_units, n_units, w.gap_words, n_seg, first_bit, table, d_out, n_symbols, w, d_count, s, 0, nullptr,
@@ -583,7 +587,7 @@ hd_status hd_decode_selfsync_finish(const uint32_t *d_units, uint64_t n_units, u
     if (st != HD_OK) return st;
     if (workspace_bytes < ws_bytes(n_units, true)) return HD_ERR_WORKSPACE;
     Workspace w = carve(d_workspace, n_units, true);
-    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, false);
+    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, false, w.sync_exit);
     bool extra = false;
     st = finish_sync(L, s, &extra);
     if (st != HD_OK) return st;
@@ -650,9 +654,9 @@ static hd_status shard_enqueue_impl(const uint32_t *d_units, uint64_t n_units_ha
     const uint64_t n_units = n_units_halo + n_units_shard;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Workspace w = carve(d_workspace, n_units, true);
-    HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes + kCtrlBytes, s));
+    HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes + w.sync_zero_bytes, s));
     const SyncLaunch L = make_sync(d_units, n_units, n_units_halo ? 0u : first_bit, table, w.gap_words, w.blk_entry,
-                                   w.changed, n_units_readable, false);
+                                   w.changed, n_units_readable, false, w.sync_exit);
     st = run_sync(L, s);
     if (st != HD_OK) return st;
     st = shard_decode(d_units, n_units_halo, n_units_shard, n_units_readable, first_bit, table, d_out, out_cap, w,
@@ -686,7 +690,7 @@ hd_status hd_decode_selfsync_shard_finish(const uint32_t *d_units, uint64_t n_un
     const uint64_t n_units = n_units_halo + n_units_shard;
     Workspace w = carve(d_workspace, n_units, true);
     const SyncLaunch L = make_sync(d_units, n_units, n_units_halo ? 0u : first_bit, table, w.gap_words, w.blk_entry,
-                                   w.changed, n_units_readable, false);
+                                   w.changed, n_units_readable, false, w.sync_exit);
     bool extra = false;
     st = finish_sync(L, s, &extra);
     if (st != HD_OK) return st;

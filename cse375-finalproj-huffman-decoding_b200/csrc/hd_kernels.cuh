@@ -133,7 +133,10 @@ struct SyncParams {
     uint8_t *cur_entry;          // per chunk: the entry offset its recorded landings were parsed from
     uint32_t *changed;           // per-round "some chunk's exit changed" counter
     uint32_t *tile_counter;      // ticket counter of the persistent K1a warps (zeroed before launch)
+    uint32_t *tile_exit;         // per K1a warp tile: kExitPublished | offset at which its parse leaves it (zeroed before launch)
 };
+constexpr uint32_t kExitPublished = 0x100u;
+constexpr uint32_t kExitWaitPolls = 1u << 16;   // bounded wait for a predecessor tile (then: flag `changed`, K1b rounds decide)
 
 // =========================================================================
 // K4: decode-and-write.  ONE persistent CTA per SM: NT decode threads (one per
@@ -625,6 +628,50 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
     uint4 *tile = reinterpret_cast<uint4 *>(smem + sync_tables_bytes(p.table.lut_bits) + (size_t)warp * kSyncTileBytes);
     const uint64_t n_units16 = (p.n_units + 3) >> 2;   // 16-byte units that hold stream data (last one may be partial)
 
+    // ---- the seam between two warp tiles.  Lane 1 of tile t entered its chunk with the exit lane 0 computed for the
+    // chunk before it, which is owned (and possibly repaired) by tile t-1.  Every tile PUBLISHES the exit of its last
+    // chunk; the warp compares the published exit of tile t-1 with what tile t assumed ONE TILE LATER, when it has long
+    // been there (tiles t-1 and t are parsed at the same time by two warps: checking right away would mean waiting).
+    // The rare mismatch (the chunk before the tile had not synchronised after 20 segments) is repaired from global
+    // memory by one lane, walking forward until the parses merge; a walk that runs through the whole tile changes an
+    // exit that is already published: `changed` is counted and the host runs K1b rounds.
+    const uint32_t kW = kSyncChunkSegs / 8;
+    uint32_t pend_tile = 0, pend_assumed = 0;   // tile whose first seam is still to be checked (0: none)
+    auto check_seam = [&]() {
+        if (pend_tile == 0) return;
+        uint32_t st = 0;
+        if (lane == 0) {
+            for (uint32_t polls = 0; polls < kExitWaitPolls; ++polls) {
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(st) : "l"(p.tile_exit + pend_tile - 1) : "memory");
+                if (st & kExitPublished) break;
+                __nanosleep(200);
+            }
+            if (!(st & kExitPublished)) {
+                atomicAdd(p.changed, 1u);   // predecessor not seen in time (never expected): the K1b rounds settle it
+            } else if ((st & 15u) != pend_assumed) {
+                const GlobalSegLoader gld{p.units, p.n_units};
+                const uint64_t c0 = (uint64_t)pend_tile * kSyncTileChunks + 1;
+                uint64_t c1 = c0 + kSyncTileChunks;
+                if (c1 > p.n_chunks) c1 = p.n_chunks;
+                uint32_t xin = st & 15u;
+                bool exit_changed = false;
+                for (uint64_t c = c0; c < c1; ++c) {
+                    uint32_t words[2] = {p.gap_words[c * kW], p.gap_words[c * kW + 1]};
+                    const bool merged = sync_repair_chunk<EXACT, LONG>(gld, c, xin, L, words);
+                    p.gap_words[c * kW] = words[0];
+                    p.gap_words[c * kW + 1] = words[1];
+                    p.cur_entry[c] = (uint8_t)xin;
+                    exit_changed = !merged;
+                    if (merged) break;
+                    xin = words[1] >> 28;
+                }
+                if (exit_changed && c1 - c0 == kSyncTileChunks) atomicAdd(p.changed, 1u);
+            }
+        }
+        __syncwarp();
+        pend_tile = 0;
+    };
+
     for (;;) {
         uint32_t ticket = 0;
         if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u);
@@ -699,7 +746,15 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
             p.cur_entry[chunk] = (uint8_t)entry;
             *reinterpret_cast<uint2 *>(p.gap_words + chunk * (kSyncChunkSegs / 8)) = make_uint2(words[0], words[1]);
         }
+        if (lane == 31 && active) {   // (a tile without a 32nd chunk is the last one: nobody reads its exit)
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p.tile_exit + ticket), "r"(kExitPublished | (words[1] >> 28)) : "memory");
+        }
+        const uint32_t assumed = __shfl_sync(0xffffffffu, words[1] >> 28, 0);   // lane 0's exit = what lane 1 was entered with
+        check_seam();   // of the tile this warp parsed BEFORE this one
+        if (ticket > 0) { pend_tile = ticket; pend_assumed = assumed; }
+        __syncwarp();   // the repair above wrote this warp's earlier results; keep the warp together before restaging
     }
+    check_seam();
 }
 
 // loads segment s from a thread-private shared-memory copy of one chunk that starts at segment seg0

@@ -68,7 +68,7 @@ def decode_gap(units, gap_words, n_segments, n_symbols, flat_lut=None, pairs=Non
 
 
 def sync(units, flat_lut=None, pairs=None, first_bit=0, exact=False):
-    """-> (gap words, rounds run, [chunks repaired in K1b round 1, K1c rounds])."""
+    """-> (gap words, K1b rounds run, [tiles whose published exit moved in K1a, K1b rounds])."""
     units = np.ascontiguousarray(units, dtype=np.uint32)
     f, fp, fb, p, pp, npairs = _tbl(flat_lut, pairs)
     n_seg = (len(units) + 3) // 4

@@ -157,11 +157,11 @@ int64_t emul_decode_gap(const uint32_t *units, uint64_t n_units, const uint32_t 
 
 }  // extern "C" (closed for the templates below)
 
-// Re-enactment of hd_sync_parse_kernel (K1a: halo + chunk per thread), the two
-// blind hd_sync_repair_kernel rounds (K1b, threads in ascending order) and, if
-// the second still changed a chunk exit, hd_sync_walk_kernel rounds (K1c).
-// Returns the number of repair/walk rounds run (>= 0) or negative on error.
-// rounds_out[0] = chunks repaired in K1b round 1, [1] = K1c rounds.
+// Re-enactment of hd_sync_parse_kernel (K1a: halo + chunk per thread, seams
+// settled inside the warp tile, tile seams checked against the published exits)
+// and, if a published exit moved afterwards, hd_sync_walk_kernel rounds (K1b).
+// Returns the number of K1b rounds run (>= 0) or negative on error.
+// rounds_out[0] = tiles whose published exit moved, [1] = K1b rounds.
 template <bool EXACT, bool LONG>
 static int64_t emul_sync_t(HostTables &h, const uint32_t *units, uint64_t n_units, uint32_t first_bit,
                            uint32_t *gap_words_out, uint32_t *rounds_out) {
@@ -200,6 +200,7 @@ static int64_t emul_sync_t(HostTables &h, const uint32_t *units, uint64_t n_unit
     std::vector<uint32_t> fin_words(gap_words_out, gap_words_out + n_chunks * kW);   // spec results of every chunk
     std::vector<uint32_t> fin_ent(ent);
     const uint64_t n_tiles_k1 = n_chunks > 1 ? (n_chunks - 1 + kSyncTileChunks - 1) / kSyncTileChunks : 1;
+    std::vector<uint32_t> published(n_tiles_k1, 0), assumed(n_tiles_k1, 0);
     for (uint64_t t = 0; t < n_tiles_k1; ++t) {
         const uint64_t t0 = t * kSyncTileChunks;
         const uint64_t t1 = t0 + 32 < n_chunks ? t0 + 32 : n_chunks;
@@ -221,6 +222,8 @@ static int64_t emul_sync_t(HostTables &h, const uint32_t *units, uint64_t n_unit
             }
             if (!any) break;
         }
+        assumed[t] = w[0][1] >> 28;                        // lane 0's exit: what lane 1 was entered with
+        if (t1 - t0 == 32) published[t] = w[31][1] >> 28;   // exit of the tile's last chunk
         for (uint64_t l = (t == 0 ? 0 : 1); l < t1 - t0; ++l) {   // owners write
             fin_words[(t0 + l) * kW] = w[l][0];
             fin_words[(t0 + l) * kW + 1] = w[l][1];
@@ -230,8 +233,33 @@ static int64_t emul_sync_t(HostTables &h, const uint32_t *units, uint64_t n_unit
     for (uint64_t i = 0; i < n_chunks * kW; ++i) gap_words_out[i] = fin_words[i];
     ent = fin_ent;
     for (uint64_t c = 0; c < n_chunks; ++c) cur_entry[c] = (uint8_t)ent[c];
-    // ---- K1b rounds: one blind round, then further ones until no group exit changes ----
-    if (rounds_out) { rounds_out[0] = 0; rounds_out[1] = 0; }
+    // ---- the seams between warp tiles, inside K1a: tile t assumed lane 0's speculative exit of chunk 31t, tile t-1
+    // PUBLISHED the real one right after settling its own seams (before any later repair of its own first seam: the
+    // earliest value a concurrent warp can read).  A mismatch is repaired by a walk through the tile; a walk that does
+    // not merge inside a full tile moves an exit that is already published and counts as changed.
+    uint32_t changed0 = 0;
+    for (uint64_t t = 1; t < n_tiles_k1; ++t) {
+        const uint64_t c0 = t * kSyncTileChunks + 1;
+        uint64_t c1 = c0 + kSyncTileChunks;
+        if (c1 > n_chunks) c1 = n_chunks;
+        uint32_t xin = published[t - 1];
+        if (xin == assumed[t]) continue;
+        bool exit_changed = false;
+        for (uint64_t c = c0; c < c1; ++c) {
+            uint32_t words[2] = {gap_words_out[c * kW], gap_words_out[c * kW + 1]};
+            const bool merged = sync_repair_chunk<EXACT, LONG>(ld, c, xin, h.L, words);
+            gap_words_out[c * kW] = words[0];
+            gap_words_out[c * kW + 1] = words[1];
+            cur_entry[c] = (uint8_t)xin;
+            exit_changed = !merged;
+            if (merged) break;
+            xin = words[1] >> 28;
+        }
+        if (exit_changed && c1 - c0 == kSyncTileChunks) ++changed0;
+    }
+    // ---- K1b rounds, only if a published exit moved: until no group exit changes ----
+    if (rounds_out) { rounds_out[0] = changed0; rounds_out[1] = 0; }
+    if (!changed0) return 0;
     int64_t rounds = 0;
     const uint64_t n_groups = (n_chunks + kSyncWalkChunksEmul - 1) / kSyncWalkChunksEmul;
     for (uint64_t r = 0; r <= n_groups + 2; ++r) {
