@@ -292,6 +292,8 @@ def ours(args):
 
     for _ in range(max(args.warmup, 3)):
         flush.add_(1)
+        if shard is not None:
+            shard.align()
         step()
         finish()
     if shard is not None:
@@ -318,6 +320,9 @@ def ours(args):
     clocks.start()
     for i in range(args.steps):
         flush.add_(1)
+        if shard is not None:
+            shard.align()   # the flush is not part of the workload: ranks whose flush took longer are waited for HERE,
+                            # outside the events, so that the timed exchange only sees the skew of the decode itself
         ev[i][0].record(stream)
         step()
         ev[i][1].record(stream)

@@ -150,6 +150,12 @@ class ShardedSelfSyncDecoder:
         else:
             self.all_info.copy_(self.info)
 
+    def align(self):
+        """Stream-side rendezvous of the ranks (one exchange round whose result nobody reads): used by bench.py after
+        the untimed L2 flush, so that a rank whose flush ran longer is not waited for inside the next timed step."""
+        if self.world > 1:
+            self._exchange()
+
     def close(self):
         if self.mailbox is not None:
             self.torch.cuda.synchronize()
@@ -173,13 +179,13 @@ class ShardedSelfSyncDecoder:
     def step(self):
         """The timed step, entirely on the stream: local shard decode (hd_decode_selfsync_shard_enqueue) + the
         exchange of {count, entry, exit}.  Several steps may be enqueued back to back (each has its own convergence
-        flag, up to 16 outstanding); call wait() before using the results."""
+        flag, up to 256 outstanding); call wait() before using the results."""
         if self._flag is None:
-            self._flag = self.torch.zeros(16, dtype=self.torch.int32).pin_memory()
-        if len(self._outstanding) >= 16:
+            self._flag = self.torch.zeros(256, dtype=self.torch.int32).pin_memory()
+        if len(self._outstanding) >= 256:
             self.wait()
         slot = self._next_slot
-        self._next_slot = (slot + 1) % 16
+        self._next_slot = (slot + 1) % 256
         self._outstanding.append(slot)
         args = self._args(0, True) + (C.c_void_p(self._flag.data_ptr() + 4 * slot), self._stream_ptr(self.torch))
         self._check(self._lib.hd_decode_selfsync_shard_enqueue(*args), "hd_decode_selfsync_shard_enqueue")
