@@ -12,6 +12,6 @@ timeout 300 python tools/prof_target.py --scheme selfsync --mib 100 --reps 3 > g
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/r1_launches_selfsync_100m.csv \
     python tools/prof_target.py --scheme selfsync --mib 100 --reps 3 > gpurun_out/ncu_ss.log 2>&1
 timeout 300 python tools/prof_target.py --scheme selfsync --mib 100 --reps 2 > gpurun_out/plain_ss2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:hd_ -s 4 -c 4 -o gpurun_out/r1_selfsync_100m \
+ncu --set full --clock-control none --import-source on -k regex:hd_ -s 2 -c 2 -o gpurun_out/r1_selfsync_100m \
     python tools/prof_target.py --scheme selfsync --mib 100 --reps 2 > gpurun_out/ncu_ss2.log 2>&1
 ls -la gpurun_out | tail -8
