@@ -403,6 +403,24 @@ def test_host_decoder_selfsync_and_huff(hd, torch_cuda):
     hdec.close()
 
 
+def test_host_decoder_falls_back_for_a_code_that_never_synchronises(hd, torch_cuda):
+    """Pipelined host decode of a stream that spans several pieces with a fixed-length 3-bit code: no piece converges
+    blind and no halo synchronises, so the chained fast path must hand over to the serial one (exact entry offsets)."""
+    torch = torch_cuda
+    pairs = cases.fixed_length_code(8, 3)
+    n = 8_000_003                                # 187 k segments: more than the first (128 k segment) piece
+    data = cases.data_for_pairs(pairs, n, seed=16)
+    units, gw, bits, lut = cases.oracle_stream(data, pairs, pad_unit=True)
+    hdec = hd.HostDecoder(len(units), n, device=0)
+    h_units = torch.from_numpy(units.view(np.int32)).pin_memory()
+    h_out = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        h_out.zero_()
+        hdec.decode_selfsync(h_units, lut, h_out, n)
+        assert np.array_equal(h_out.numpy(), data)
+    hdec.close()
+
+
 def test_profile_hooks_report_kernel_times(hd, torch_cuda):
     n = 2_000_000
     data = O.generate(n, 0.5, seed=61)
