@@ -32,7 +32,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "gpuhd self-sync decode, 100 MiB generate.cpp r=0.5 per GPU (./bin/demo 0 100 shape)"
+def workload(args):
+    """configs[1] of BASELINE.json by default; --mib / --redundancy name the other sizes (e.g. --gpus 8 --mib 1024 =
+    configs[3], the 8 GB stream sharded over the box)."""
+    return "gpuhd self-sync decode, %d MiB generate.cpp r=%g per GPU (./bin/demo 0 %d shape)" % (args.mib, args.redundancy, args.mib)
 METRIC = "decoded GB/s (device-timed)"
 FLUSH_BYTES = 256 << 20   # > 126 MB L2
 
@@ -201,7 +204,7 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": round(value, 6), "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "scheme": "cpu", "redundancy": args.redundancy},
+        "config": {"workload": workload(args), "scheme": "cpu", "redundancy": args.redundancy},
         "cpu_baseline": {"value": round(value, 6), "unit": "GB/s", "cores": cores, "kind": kind,
                          "sample": "each step decodes a %d MiB sample of the workload with %s; host CPU only"
                                    % (sample_mib, what)},
@@ -405,7 +408,7 @@ def ours(args):
         "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "scheme": "selfsync", "mib_per_gpu": args.mib, "redundancy": args.redundancy,
+        "config": {"workload": workload(args), "scheme": "selfsync", "mib_per_gpu": args.mib, "redundancy": args.redundancy,
                    "subsequence_bits": 128, "max_codeword_length": 11, "n_symbols_total": int(n_total),
                    "n_units_total": int(len(units)), "l2": "flushed between steps (256 MiB write, outside the events)",
                    "parallelism": "shard%d" % world,
