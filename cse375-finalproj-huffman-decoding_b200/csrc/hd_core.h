@@ -15,6 +15,9 @@
 #define HD_HD inline
 #endif
 
+#ifndef HD_TWO_STEP
+#define HD_TWO_STEP 1   // decode_chunk: two table steps per window slide (measured)
+#endif
 #ifndef HD_WHATIF
 #define HD_WHATIF 0   // developer timing experiments (tools/whatif.sh); 0 in every shipped build
 #endif
@@ -124,13 +127,41 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
         if (LONG) {
             if ((e >> 16) == 0) e = resolve_long(win, T.lut_bits, T.lt, T.order);
         }
-        const uint32_t u = A | kColBits;
+        uint32_t u = A | kColBits;
 #if !(HD_WHATIF & 2)
         smem_st_u8(A, e, arena);
         smem_st_u8(((u + 1u) & ~kColBits) | col, e >> 8, arena);
 #endif
         A = ((u + (e >> 24)) & ~kColBits) | col;
-        const uint32_t np = pos + byte2(e);
+        uint32_t np = pos + byte2(e);
+#if HD_TWO_STEP
+        // Second table step from the same 32-bit window: a step consumes at most 16 bits, so the 16 bits the next one
+        // looks at are still there (win << nbits).  One window slide, loop test and branch per TWO lookups, and the
+        // loop-carried chain between the two loads is shift -> index -> load instead of add -> slide -> funnel -> index
+        // -> load.  The step is dropped when the first one already reached `stop`.
+        {
+            const uint32_t win2 = win << byte2(e);
+            uint32_t e2 = T.lut[win2 >> T.idx_shift];
+            if (LONG) {
+                if ((e2 >> 16) == 0) e2 = resolve_long(win2, T.lut_bits, T.lt, T.order);
+            }
+            if (np < stop) {
+                e = e2;
+#if defined(__CUDA_ARCH__)
+                asm volatile("");
+#endif
+            } else {
+                e2 = 0;
+            }
+            u = A | kColBits;
+#if !(HD_WHATIF & 2)
+            smem_st_u8(A, e2, arena);
+            smem_st_u8(((u + 1u) & ~kColBits) | col, e2 >> 8, arena);
+#endif
+            A = ((u + (e2 >> 24)) & ~kColBits) | col;
+            np += byte2(e2);
+        }
+#endif
 #if defined(__CUDA_ARCH__)
         // Crossed a unit boundary: slide the window and fetch the word after it.  One asm block with its own predicate,
         // so that the slide stays predicated moves (FMA pipe; the INT pipe bounds this loop) and the load writes w2 IN
