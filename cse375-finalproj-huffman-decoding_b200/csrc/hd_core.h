@@ -88,6 +88,18 @@ HD_HD uint32_t byte2(uint32_t e) {
 #endif
 }
 
+// a + k as a multiply-add with an OPAQUE multiplier register holding 1: it issues on the FMA pipe.  The decode loop is
+// bound by the INT (ALU) pipe, which retires one warp instruction every two cycles; written as an add the compiler
+// puts it there (VIADD).  (The same trick for the two shifts of a table step, mad.hi by an opaque power of two, was
+// measured and is slower: IMAD.HI is not a cheap instruction.)
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t one, uint32_t k) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(one), "r"(k), "r"(a));
+    return d;
+}
+#endif
+
 // Decode one chunk (SEGS consecutive 128-bit segments of one thread) in a single
 // flattened loop.  The chunk's units sit in the thread's column of the
 // transposed input tile: word w at in_col[w * NT] (conflict-free
@@ -121,6 +133,11 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
     uint32_t A = stage_addr;
     uint32_t pos = entry;
     uint32_t e = 0;
+#if defined(__CUDA_ARCH__)
+#define HD_PLUS1(u_) add_fma((u_), T.one, 1u)
+#else
+#define HD_PLUS1(u_) ((u_) + 1u)
+#endif
     while (pos < stop) {
         const uint32_t win = funnel_l(w1, w0, pos);   // next 32 stream bits
         e = T.lut[win >> T.idx_shift];
@@ -130,7 +147,7 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
         uint32_t u = A | kColBits;
 #if !(HD_WHATIF & 2)
         smem_st_u8(A, e, arena);
-        smem_st_u8(((u + 1u) & ~kColBits) | col, e >> 8, arena);
+        smem_st_u8((HD_PLUS1(u) & ~kColBits) | col, e >> 8, arena);
 #endif
         A = ((u + (e >> 24)) & ~kColBits) | col;
         uint32_t np = pos + byte2(e);
@@ -156,7 +173,7 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
             u = A | kColBits;
 #if !(HD_WHATIF & 2)
             smem_st_u8(A, e2, arena);
-            smem_st_u8(((u + 1u) & ~kColBits) | col, e2 >> 8, arena);
+            smem_st_u8((HD_PLUS1(u) & ~kColBits) | col, e2 >> 8, arena);
 #endif
             A = ((u + (e2 >> 24)) & ~kColBits) | col;
             np += byte2(e2);
@@ -191,6 +208,7 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
 #endif
         pos = np;
     }
+#undef HD_PLUS1
     uint32_t cnt = (((A - stage_addr) >> row_shift(NT)) << 2) | (A & 3u);
     // the second symbol of the last lookup starts exactly at `stop`: it is the successor's first symbol
     if (pos > stop && (e >> 24) == 2u) --cnt;
