@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
         // ---- seams inside the warp tile: a lane whose halo parse had not merged yet (~20 % at the reference's
         // redundancy 0.5) re-parses the head of its chunk from its left neighbour's landing, from the staged
         // tile; repeated until no lane changes (a parse that fails to merge inside a chunk moves on one lane per
-        // round).  After this the tile is consistent given the entry of its FIRST chunk; K1b checks that one.
+        // round).  After this the tile is consistent given the entry of its FIRST owned chunk; check_seam() looks at that one.
         const TileSegLoader tld{tile, q0};
         for (;;) {
             const uint32_t left = __shfl_up_sync(0xffffffffu, words[1] >> 28, 1);
