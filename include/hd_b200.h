@@ -122,12 +122,12 @@ hd_status hd_decode_selfsync(const uint32_t *d_units, uint64_t n_units,
                              size_t workspace_bytes, void *stream);
 
 /* The same decode split in two for callers that overlap it with other work:
- * _enqueue puts everything (one memset, K1a, K1b, K4, the 4-byte copy of
- * the convergence counter into *h_unconverged -- pinned host memory) on
+ * _enqueue puts everything (one memset, K1a, K4, the 4-byte copy of the
+ * convergence counter into *h_unconverged -- pinned host memory) on
  * `stream` and returns without synchronising; _finish synchronises the stream
  * and, in the rare case that *h_unconverged != 0 (a parse that did not
- * synchronise within 64 Kbit), iterates K1b to the fixed point and decodes
- * again.  hd_decode_selfsync[_ex] == _enqueue + _finish. */
+ * synchronise within a 64 Kbit warp tile), iterates K1b to the fixed point
+ * and decodes again.  hd_decode_selfsync[_ex] == _enqueue + _finish. */
 hd_status hd_decode_selfsync_enqueue(const uint32_t *d_units, uint64_t n_units,
                                      uint32_t first_bit, const hd_table *table,
                                      uint8_t *d_out, uint64_t n_symbols,
