@@ -8,7 +8,9 @@ Metric (BASELINE.json): decoded GB/s, device-timed.  A "step" = one complete dec
 (self-synchronisation scheme, `./bin/demo 0 100` shape: 100 MiB of generate.cpp data at redundancy 0.5 per GPU,
 llhuff <=11-bit canonical code, 128-bit subsequences).  At N>1 ONE stream of N x 100 MiB is sharded on
 subsequence boundaries (weak scaling: per-GPU work fixed); each rank decodes its shard independently and only the
-per-rank symbol counts / seam offsets are all-gathered (NCCL) inside the timed region.
+per-rank symbol counts / seam offsets are exchanged inside the timed region (peer-memory mailbox over NVLink,
+hd_mailbox_*; NCCL all-gather where CUDA IPC is not available).  --mib / --redundancy select the other BASELINE sizes
+(e.g. --gpus 8 --mib 1024: the 8 GB stream of configs[3]).
 
   value     n_symbols(all ranks) / device time (CUDA events on the decode stream, max over ranks), inputs in HBM
   e2e       same metric through the host-buffer C-ABI call (hd_host_decode_selfsync): pinned host -> H2D -> decode
