@@ -238,6 +238,27 @@ class ShardedSelfSyncDecoder:
                                                 self.n_symbols))
         return total == self.n_symbols and bool(self.torch.equal(self.out[:self.count_local], want))
 
+    def gather_output(self, dst=0):
+        """Optional last step: collect the sharded output on rank `dst` over NVLink.  finish() must have
+        placed the outputs (every rank knows all counts and offsets).  Point-to-point NCCL sends of each rank's bytes
+        straight into their place in the destination buffer; returns the whole output on `dst`, None elsewhere."""
+        torch, dist = self.torch, self.dist
+        infos = self.all_info.cpu().numpy().reshape(self.world, 3)
+        placed = place_outputs(infos[:, 0], self.n_symbols)
+        if self.world == 1 or dist is None:
+            return self.out[:self.count_local]
+        if self.rank == dst:
+            whole = torch.empty(self.n_symbols, dtype=torch.uint8, device="cuda")
+            off, cnt = placed[dst]
+            whole[off:off + cnt].copy_(self.out[:cnt])
+            reqs = [dist.irecv(whole[o:o + c], src=r) for r, (o, c) in enumerate(placed) if r != dst and c]
+            for q in reqs:
+                q.wait()
+            return whole
+        if self.count_local:
+            dist.send(self.out[:self.count_local], dst=dst)
+        return None
+
     def e2e(self, data, steps=5):
         """Host-buffer path: pinned shard -> H2D -> decode + all-gather -> D2H, wall clock, max over ranks."""
         import time
