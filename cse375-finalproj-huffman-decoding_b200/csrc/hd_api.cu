@@ -13,6 +13,7 @@
 #include <new>
 
 #include "hd_kernels.cuh"
+#include "hd_decode.cuh"
 #include "hd_tables.cuh"
 #include "hd_encoder.cuh"
 #include "hd_mailbox.cuh"
@@ -237,12 +238,116 @@ hd_status launch_decode_geom(const DecodeGeom &g, const DecodeParams &p, cudaStr
     }
 }
 
+// ---- K4 "warp tile" kernel (hd_decode.cuh): geometry + launch ---------------------------------------------------
+// segs = segments per decode thread, rcap = register rows of the in-place compaction (kernel template parameters),
+// stage_rows = rows of one staging buffer of a warp block, n_warps = decode warps per CTA.
+struct TileGeom {
+    int segs = 0, rcap = 0;
+    uint32_t stage_rows = 0, n_warps = 0;
+    size_t smem = 0;
+};
+constexpr uint32_t kTileMaxWarps = 27;    // (27 + 1 scan warp) * 32 = 896 threads: 72 registers per thread
+constexpr size_t kTileStaticSmem = 1024;  // static __shared__ of the kernel + alignment slack of the warp blocks
+
+bool tile_geom(const hd_table *t, int segs, int max_smem, uint32_t want_warps, TileGeom &g) {
+    const uint32_t min_len = std::max<uint32_t>(1, t->host.min_len);
+    // a chunk decodes bits [entry, 128*segs + next_entry), offsets <= 15; decode_chunk may store one symbol more than
+    // it counts (second symbol of the last lookup) and always writes the second byte of a lookup
+    const uint32_t max_cnt = (kSegmentBits * segs + 15 + min_len - 1) / min_len;
+    const uint32_t rows_used = (max_cnt + 3) / 4;
+    g.segs = segs;
+    g.stage_rows = max_cnt / 4 + 3;
+    g.rcap = rows_used <= 12 ? 12 : rows_used <= 24 ? 24 : rows_used <= 36 ? 36 : 0;
+    if (!g.rcap) return false;
+    if ((segs == 2 && g.rcap == 36) || (segs == 4 && g.rcap != 24)) return false;   // not instantiated
+    const size_t tab = (4u << t->host.lut_bits) + (t->host.has_long ? 256 + align_up(sizeof(LongTables), 16) : 0);
+    const size_t warp_bytes = (size_t)(4 * segs + 2 + 2 * g.stage_rows) * kWarpRowBytes;
+    if ((size_t)max_smem < tab + kTileStaticSmem + warp_bytes) return false;
+    const size_t fit = ((size_t)max_smem - tab - kTileStaticSmem) / warp_bytes;
+    g.n_warps = (uint32_t)std::min<size_t>(fit, want_warps ? want_warps : kTileMaxWarps);
+    g.n_warps = std::min(g.n_warps, kTileMaxWarps);
+    if (g.n_warps * 32u * (uint32_t)segs < kTileThreads) return false;   // the workspace holds one status word per 256 segments
+    g.smem = tab + kWarpRowBytes + g.n_warps * warp_bytes;
+    return true;
+}
+
+int g_tile_segs = 0, g_tile_warps = 0;   // hd_set_tuning: 0 = automatic
+
+bool pick_tile_geom(const hd_table *t, int max_smem, TileGeom &g) {
+    if (g_tile_segs && tile_geom(t, g_tile_segs, max_smem, (uint32_t)g_tile_warps, g)) return true;
+    // Two segments per thread when at least 20 decode warps fit (the per-step work of a warp is amortised over twice
+    // the symbols), else one segment per thread (short minimum code length: the worst-case staging of two does not
+    // leave enough warps to hide the table latency).
+    TileGeom g2, g1;
+    const bool ok2 = tile_geom(t, 2, max_smem, (uint32_t)g_tile_warps, g2);
+    const bool ok1 = tile_geom(t, 1, max_smem, (uint32_t)g_tile_warps, g1);
+    if (ok2 && (g2.n_warps >= 20 || !ok1)) { g = g2; return true; }
+    if (ok1) { g = g1; return true; }
+    return false;
+}
+
+template <int SEGS, int RCAP, bool LONG>
+hd_status launch_tiles(const TileParams &p, size_t smem, cudaStream_t s) {
+    auto kern = hd_decode_tiles_kernel<SEGS, RCAP, LONG>;
+    HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint64_t grid = (uint64_t)device_info().sm_count;   // persistent: one CTA per SM, all co-resident (the look-back spins)
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    kern<<<(unsigned)grid, (p.n_warps + 1) * 32, smem, s>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+template <bool LONG>
+hd_status launch_tiles_geom(const TileGeom &g, const TileParams &p, cudaStream_t s) {
+    switch (g.segs * 100 + g.rcap) {
+        case 112: return launch_tiles<1, 12, LONG>(p, g.smem, s);
+        case 124: return launch_tiles<1, 24, LONG>(p, g.smem, s);
+        case 136: return launch_tiles<1, 36, LONG>(p, g.smem, s);
+        case 212: return launch_tiles<2, 12, LONG>(p, g.smem, s);
+        case 224: return launch_tiles<2, 24, LONG>(p, g.smem, s);
+        case 424: return launch_tiles<4, 24, LONG>(p, g.smem, s);
+    }
+    return HD_ERR_INVALID;
+}
+
+bool use_legacy_k4() {
+    static const bool v = [] { const char *e = getenv("HD_K4_LEGACY"); return e && *e == '1'; }();
+    return v;
+}
+
 hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32_t *d_gap_words,
                          uint64_t n_segments, uint32_t first_bit, const hd_table *table, uint8_t *d_out,
                          uint64_t n_symbols, const Workspace &w, uint64_t *d_count, cudaStream_t s,
                          uint64_t n_units_readable = 0, const uint32_t *entry_word = nullptr,
                          uint64_t *shard_info = nullptr, bool already_zeroed = false,
                          const uint64_t *d_off_in = nullptr, uint64_t *d_off_out = nullptr) {
+    if (!use_legacy_k4()) {
+        TileGeom g;
+        if (!pick_tile_geom(table, device_info().max_smem_optin, g)) return HD_ERR_INVALID;
+        TileParams q;
+        q.units = d_units;
+        q.n_units = n_units_readable > n_units ? n_units_readable : n_units;
+        q.gap_words = d_gap_words;
+        q.n_segments = n_segments;
+        q.first_bit = first_bit;
+        q.entry_word = entry_word;
+        q.shard_info = shard_info;
+        q.table = table_dev(table);
+        q.out = d_out;
+        q.n_symbols = n_symbols;
+        q.out_offset_in = d_off_in;
+        q.out_offset_out = d_off_out;
+        q.tile_status = w.tile_status;
+        q.tile_counter = w.tile_counter;
+        q.n_tiles = div_up(div_up(n_segments, (uint64_t)g.segs), (uint64_t)g.n_warps * 32);
+        q.count_out = d_count;
+        q.stage_rows = g.stage_rows;
+        q.n_warps = g.n_warps;
+        if (!already_zeroed) HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes, s));
+        ProfScope prof(HD_PROFILE_DECODE_WRITE, s);
+        return table->host.has_long ? launch_tiles_geom<true>(g, q, s) : launch_tiles_geom<false>(g, q, s);
+    }
     DecodeParams p;
     p.out_offset_in = d_off_in;
     p.out_offset_out = d_off_out;
@@ -875,6 +980,9 @@ void hd_set_trace(void *d_buf) { g_trace = static_cast<unsigned long long *>(d_b
 void hd_set_tuning(int segs_per_thread, int threads_per_tile) {
     g_force_segs = segs_per_thread;
     g_force_nt = threads_per_tile;
+    // warp-tile kernel: threads_per_tile = decode threads per CTA (a multiple of 32, at most 27 warps)
+    g_tile_segs = segs_per_thread;
+    g_tile_warps = (threads_per_tile > 0 && threads_per_tile % 32 == 0 && threads_per_tile <= (int)kTileMaxWarps * 32) ? threads_per_tile / 32 : 0;
 }
 
 // ---------------------------------------------------------------- profiling

@@ -78,7 +78,7 @@ inline void smem_st_u8(uint32_t a, uint32_t v, uint8_t *arena) { arena[a] = (uin
 #define HD_CONSTEXPR constexpr
 #endif
 HD_CONSTEXPR uint32_t col_bits(uint32_t nt) { return (nt - 1u) << 2; }
-HD_CONSTEXPR uint32_t row_shift(uint32_t nt) { return nt == 512 ? 11u : nt == 256 ? 10u : nt == 128 ? 9u : 0u; }
+HD_CONSTEXPR uint32_t row_shift(uint32_t nt) { return nt == 512 ? 11u : nt == 256 ? 10u : nt == 128 ? 9u : nt == 32 ? 7u : 0u; }
 
 HD_HD uint32_t byte2(uint32_t e) {
 #if defined(__CUDA_ARCH__)
@@ -265,6 +265,68 @@ HD_HD void compact_to_tile(const uint32_t *src, uint32_t stride, uint32_t c, uin
         if (tail > 1u) d8[1] = (uint8_t)(v >> 8);
         if (tail > 2u) d8[2] = (uint8_t)(v >> 16);
     }
+}
+
+// ---- warp-private staging blocks (K4 "warp tile" kernel) ------------------------
+// A decode warp owns a block of `rows` rows of 32 words: lane l's symbols sit in
+// column l (word m of the lane at word index m * 32 + l, little-endian bytes) --
+// the layout decode_chunk<32> writes.  The block is compacted IN PLACE: every
+// lane first pulls its whole column into registers (column_read), the warp
+// synchronises, then every lane writes its c symbols to byte offset D of the
+// same block (column_write), D = 16-byte phase of the warp's global destination
+// + the exclusive prefix of the lanes' counts -- after which the warp's span is
+// one contiguous run that a TMA bulk store flushes.  No separate output tile.
+//
+// column_write stores whole 32-bit words (one funnel shift each) from the first
+// word-aligned byte on, INCLUDING a last partial word: its surplus bytes land on
+// the head bytes of the following lane(s), which is why the <= 3 head bytes of
+// every lane are written by column_write_head AFTER a second warp
+// synchronisation.  (A lane whose symbols all fit before the first word boundary
+// writes nothing but head bytes.)  Surplus bytes of the last lane fall into the
+// slack behind the warp's span.  w[] must hold RCAP + 2 words; words past the
+// lane's rows may be garbage (they only reach bytes nobody keeps).
+template <int RCAP>
+HD_HD void column_read(const uint32_t *col, uint32_t rows_max, uint32_t (&w)[RCAP + 2]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int g = 0; g < RCAP; g += 4) {
+        if ((uint32_t)g < rows_max) {   // warp-uniform: whole groups are skipped, not predicated off
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int i = g; i < g + 4 && i < RCAP; ++i) w[i] = col[i * 32];
+        }
+    }
+}
+
+template <int RCAP>
+HD_HD void column_write(const uint32_t (&w)[RCAP + 2], uint32_t c, uint8_t *blk, uint32_t D, uint32_t rows_max) {
+    uint32_t head = (4u - (D & 3u)) & 3u;
+    if (head > c) head = c;
+    const uint32_t nw = (c - head + 3u) >> 2;   // words incl. the partial last one
+    uint32_t *dst = reinterpret_cast<uint32_t *>(blk + D + head);
+    const uint32_t sh = 8u * head;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int g = 0; g < RCAP; g += 4) {
+        if ((uint32_t)g < rows_max) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int i = g; i < g + 4 && i < RCAP; ++i)
+                if ((uint32_t)i < nw) dst[i] = funnel_r(w[i], w[i + 1], sh);
+        }
+    }
+}
+
+HD_HD void column_write_head(uint32_t w0, uint32_t c, uint8_t *blk, uint32_t D) {
+    uint32_t head = (4u - (D & 3u)) & 3u;
+    if (head > c) head = c;
+    if (head > 0u) blk[D] = (uint8_t)w0;
+    if (head > 1u) blk[D + 1] = (uint8_t)(w0 >> 8);
+    if (head > 2u) blk[D + 2] = (uint8_t)(w0 >> 16);
 }
 
 // ---------------------------------------------------------------- sync side

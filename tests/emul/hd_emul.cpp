@@ -3,6 +3,7 @@
 // block/tile structure re-enacted sequentially, so that control-flow and table
 // bugs are caught in this GPU-less container.  Never linked into the product
 // library; the product has no CPU path.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -141,6 +142,77 @@ static int64_t emul_decode_gap_nt(HostTables &h, const uint32_t *units, uint64_t
     return (int64_t)(base < n_symbols ? base : n_symbols);
 }
 
+// Re-enactment of hd_decode_tiles_kernel<SEGS, RCAP> (hd_decode.cuh): warp tiles of 32 chunks; per lane: transposed
+// input column, decode_chunk<32> into the warp's staging block, then the IN-PLACE compaction exactly as the kernel
+// orders it (all lanes column_read -> all lanes column_write -> all lanes column_write_head) at the 16-byte phase of
+// the warp's destination, copy out.
+template <int RCAP>
+static int64_t emul_decode_tiles(HostTables &h, const uint32_t *units, uint64_t n_units, const uint32_t *gap_words,
+                                 uint64_t n_segments, uint32_t first_bit, uint8_t *out, uint64_t n_symbols,
+                                 uint64_t out_addr_phase, uint32_t segs) {
+    const uint32_t min_len = h.blob.min_len ? h.blob.min_len : 1;
+    const uint32_t max_cnt = (kSegmentBits * segs + 15 + min_len - 1) / min_len;
+    const uint32_t stage_rows = max_cnt / 4 + 3;
+    if ((max_cnt + 3) / 4 > (uint32_t)RCAP) return -4;
+    const uint32_t in_rows = 4 * segs + 2;
+    std::vector<uint32_t> in((size_t)in_rows * 32);
+    std::vector<uint8_t> arena((size_t)(stage_rows + 2) * 128);
+    const uint32_t stage_off = 128;
+    auto nib = [&](uint64_t j) { return (gap_words[j >> 3] >> (4u * (uint32_t)(j & 7))) & 15u; };
+    const uint64_t n_chunks = (n_segments + segs - 1) / segs;
+    const uint64_t n_wtiles = (n_chunks + 31) / 32;
+    uint64_t base = 0;
+    for (uint64_t wt = 0; wt < n_wtiles; ++wt) {
+        std::fill(arena.begin(), arena.end(), (uint8_t)0xDE);
+        std::fill(in.begin(), in.end(), 0xBADC0DEu);
+        uint32_t cnt[32];
+        for (uint32_t l = 0; l < 32; ++l) {
+            const uint64_t g0 = (wt * 32 + l) * segs;
+            cnt[l] = 0;
+            if (g0 >= n_segments) continue;
+            const uint64_t left = n_segments - g0;
+            const uint32_t nseg = left < segs ? (uint32_t)left : segs;
+            uint32_t *col = in.data() + l;
+            for (uint32_t w = 0; w < in_rows; ++w) {
+                const uint64_t u = g0 * 4 + w;
+                col[(size_t)w * 32] = u < n_units ? units[u] : 0u;
+            }
+            const uint32_t entry = g0 == 0 ? first_bit : nib(g0 - 1);
+            const uint32_t stop = nseg * kSegmentBits + nib(g0 + nseg - 1);
+            const uint32_t sa = stage_off + l * 4u;
+            const uint32_t c = h.blob.has_long ? decode_chunk<32, true>(col, entry, stop, h.T, sa, arena.data())
+                                               : decode_chunk<32, false>(col, entry, stop, h.T, sa, arena.data());
+            if (c > max_cnt) return -2;
+            cnt[l] = c;
+        }
+        for (uint32_t i = 0; i < 128; ++i)   // canary row behind the staging rows
+            if (arena[(size_t)stage_off + (size_t)stage_rows * 128 + i] != 0xDE) return -6;
+        uint8_t *sblk = arena.data() + stage_off;
+        uint32_t wtot = 0, rows_max = 0;
+        for (uint32_t l = 0; l < 32; ++l) { wtot += cnt[l]; rows_max = std::max(rows_max, (cnt[l] + 3) / 4); }
+        const uint64_t lim = base >= n_symbols ? 0 : n_symbols - base;
+        const uint32_t total = wtot < lim ? wtot : (uint32_t)lim;
+        const uint32_t phase = (uint32_t)((out_addr_phase + base) & 15u);
+        if (phase + wtot + 4 > stage_rows * 128u) return -3;   // compacted span + surplus of the last word must fit
+        uint32_t w[32][RCAP + 2], c[32], excl[32];
+        uint32_t e = 0;
+        for (uint32_t l = 0; l < 32; ++l) {
+            excl[l] = e;
+            e += cnt[l];
+            c[l] = cnt[l];
+            if (excl[l] >= total) c[l] = 0;
+            else if (excl[l] + c[l] > total) c[l] = total - excl[l];
+            for (int i = 0; i < RCAP + 2; ++i) w[l][i] = 0;
+            column_read<RCAP>(reinterpret_cast<const uint32_t *>(sblk) + l, rows_max, w[l]);
+        }
+        for (uint32_t l = 0; l < 32; ++l) column_write<RCAP>(w[l], c[l], sblk, phase + excl[l], rows_max);
+        for (uint32_t l = 0; l < 32; ++l) column_write_head(w[l][0], c[l], sblk, phase + excl[l]);
+        std::memcpy(out + base, sblk + phase, total);
+        base += wtot;
+    }
+    return (int64_t)(base < n_symbols ? base : n_symbols);
+}
+
 extern "C" {
 
 int64_t emul_decode_gap(const uint32_t *units, uint64_t n_units, const uint32_t *gap_words, uint64_t n_segments,
@@ -151,6 +223,12 @@ int64_t emul_decode_gap(const uint32_t *units, uint64_t n_units, const uint32_t 
     if (!make_tables(flat, flat_bits, pairs, n_pairs, h)) return -1;
     if (segs != 1 && segs != 2 && segs != 4) return -4;
     if (nt == 256) return emul_decode_gap_nt<256>(h, units, n_units, gap_words, n_segments, first_bit, out, n_symbols, out_addr_phase, segs);
+    if (nt == 32) {
+        int64_t r = emul_decode_tiles<12>(h, units, n_units, gap_words, n_segments, first_bit, out, n_symbols, out_addr_phase, segs);
+        if (r == -4) r = emul_decode_tiles<24>(h, units, n_units, gap_words, n_segments, first_bit, out, n_symbols, out_addr_phase, segs);
+        if (r == -4 && segs == 1) r = emul_decode_tiles<36>(h, units, n_units, gap_words, n_segments, first_bit, out, n_symbols, out_addr_phase, segs);
+        return r == -4 ? -40 : r;   // -40: geometry not instantiated for this code (mirrors tile_geom in hd_api.cu)
+    }
     if (nt == 512) return emul_decode_gap_nt<512>(h, units, n_units, gap_words, n_segments, first_bit, out, n_symbols, out_addr_phase, segs);
     return -4;
 }
