@@ -6,6 +6,7 @@
 #define HD_CORE_H_
 
 #include <stdint.h>
+#include <string.h>
 
 #include "hd_internal.h"
 
@@ -65,8 +66,18 @@ struct DecodeTables {
 __device__ __forceinline__ void smem_st_u8(uint32_t a, uint32_t v, uint8_t *) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v));
 }
+__device__ __forceinline__ void smem_st_u32(uint32_t a, uint32_t v, uint8_t *) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v));
+}
+__device__ __forceinline__ uint32_t smem_ld_u32(uint32_t a, const uint8_t *) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
 #else
 inline void smem_st_u8(uint32_t a, uint32_t v, uint8_t *arena) { arena[a] = (uint8_t)v; }
+inline void smem_st_u32(uint32_t a, uint32_t v, uint8_t *arena) { memcpy(arena + a, &v, 4); }
+inline uint32_t smem_ld_u32(uint32_t a, const uint8_t *arena) { uint32_t v; memcpy(&v, arena + a, 4); return v; }
 #endif
 
 // Staging/input tiles are TRANSPOSED: with NT decode threads per tile, thread t
@@ -285,8 +296,10 @@ HD_HD void compact_to_tile(const uint32_t *src, uint32_t stride, uint32_t c, uin
 // writes nothing but head bytes.)  Surplus bytes of the last lane fall into the
 // slack behind the warp's span.  w[] must hold RCAP + 2 words; words past the
 // lane's rows may be garbage (they only reach bytes nobody keeps).
+// Addresses are shared-window addresses on the device (explicit LDS/STS, no generic-pointer conversion per access)
+// and arena offsets in the CPU emulator, as for decode_chunk.
 template <int RCAP>
-HD_HD void column_read(const uint32_t *col, uint32_t rows_max, uint32_t (&w)[RCAP + 2]) {
+HD_HD void column_read(uint32_t col_addr, uint32_t rows_max, uint32_t (&w)[RCAP + 2], const uint8_t *arena) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -295,17 +308,18 @@ HD_HD void column_read(const uint32_t *col, uint32_t rows_max, uint32_t (&w)[RCA
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int i = g; i < g + 4 && i < RCAP; ++i) w[i] = col[i * 32];
+            for (int i = g; i < g + 4 && i < RCAP; ++i) w[i] = smem_ld_u32(col_addr + (uint32_t)i * 128u, arena);
         }
     }
 }
 
+// D = byte address of the lane's first symbol in the compacted block
 template <int RCAP>
-HD_HD void column_write(const uint32_t (&w)[RCAP + 2], uint32_t c, uint8_t *blk, uint32_t D, uint32_t rows_max) {
+HD_HD void column_write(const uint32_t (&w)[RCAP + 2], uint32_t c, uint32_t D, uint32_t rows_max, uint8_t *arena) {
     uint32_t head = (4u - (D & 3u)) & 3u;
     if (head > c) head = c;
     const uint32_t nw = (c - head + 3u) >> 2;   // words incl. the partial last one
-    uint32_t *dst = reinterpret_cast<uint32_t *>(blk + D + head);
+    const uint32_t dst = D + head;
     const uint32_t sh = 8u * head;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -316,17 +330,17 @@ HD_HD void column_write(const uint32_t (&w)[RCAP + 2], uint32_t c, uint8_t *blk,
 #pragma unroll
 #endif
             for (int i = g; i < g + 4 && i < RCAP; ++i)
-                if ((uint32_t)i < nw) dst[i] = funnel_r(w[i], w[i + 1], sh);
+                if ((uint32_t)i < nw) smem_st_u32(dst + 4u * (uint32_t)i, funnel_r(w[i], w[i + 1], sh), arena);
         }
     }
 }
 
-HD_HD void column_write_head(uint32_t w0, uint32_t c, uint8_t *blk, uint32_t D) {
+HD_HD void column_write_head(uint32_t w0, uint32_t c, uint32_t D, uint8_t *arena) {
     uint32_t head = (4u - (D & 3u)) & 3u;
     if (head > c) head = c;
-    if (head > 0u) blk[D] = (uint8_t)w0;
-    if (head > 1u) blk[D + 1] = (uint8_t)(w0 >> 8);
-    if (head > 2u) blk[D + 2] = (uint8_t)(w0 >> 16);
+    if (head > 0u) smem_st_u8(D, w0, arena);
+    if (head > 1u) smem_st_u8(D + 1u, w0 >> 8, arena);
+    if (head > 2u) smem_st_u8(D + 2u, w0 >> 16, arena);
 }
 
 // ---------------------------------------------------------------- sync side

@@ -70,6 +70,27 @@ __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
     return r;
 }
 
+// waits for a phase of a shared-memory barrier; the hint lets the hardware keep the warp suspended for up to ~10 us per
+// attempt instead of returning (and being re-issued) every few hundred cycles
+__device__ __forceinline__ void mbar_wait_suspended(unsigned long long *bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(a), "r"(parity), "r"(10000u)
+                     : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ uint32_t smem_ld_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void tma_bulk_store_s(void *gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+
 template <int SEGS, int RCAP, bool LONG>
 __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -97,9 +118,10 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
 
     __shared__ uint32_t s_wtot[2][32];   // warp totals of the tile in buffer b; the scan warp turns them into exclusive offsets
     __shared__ uint32_t s_tileid[3];     // ring: tile of step k in slot k % 3
-    __shared__ unsigned long long s_base[2];
+    __shared__ unsigned long long s_gbase[2];   // global ADDRESS at which the tile in buffer b starts (out + exclusive prefix)
+    __shared__ uint32_t s_lim[2];               // symbols of the output capacity left at that address (saturated to 32 bits)
     __shared__ uint32_t s_sum[2], s_arrived[2];   // tile total / number of warps that added theirs
-    // s_ready[b] completes its n-th phase once the prefix of step k = b + 2n is in s_base[b].  Parity waits are safe:
+    // s_ready[b] completes its n-th phase once the prefix of step k = b + 2n is in s_gbase[b] / s_lim[b].  Parity waits are safe:
     // the scan warp cannot finish step k+2 (the next phase of the same barrier) before every decode warp has arrived
     // at FULL of step k+1, i.e. has long left its wait for step k.
     __shared__ __align__(8) unsigned long long s_ready[2];
@@ -156,7 +178,9 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
                 if (lane == 0) red_max_gpu_u64(p.tile_status + tile * kStatusStride, kFlagPrefix | (excl + agg));
             }
             if (lane == 0) {
-                s_base[b] = excl;
+                s_gbase[b] = (unsigned long long)(uintptr_t)(out + excl);
+                const uint64_t left = excl < n_symbols ? n_symbols - excl : 0ull;
+                s_lim[b] = left > 0xffffffffull ? 0xffffffffu : (uint32_t)left;
                 if (tile + 1 == p.n_tiles) {
                     uint64_t tot = excl + agg;
                     tot = tot < n_symbols ? tot : n_symbols;
@@ -187,13 +211,16 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
     T.lt = s_long;
     T.order = s_order;
     const uint32_t blk_abs = blocks_abs + warp * warp_bytes;
-    uint8_t *const blk = smem + (blk_abs - smem_abs);
-    uint32_t *const col = reinterpret_cast<uint32_t *>(blk) + lane;   // this lane's input column
+    const uint32_t col_abs = blk_abs + lane * 4u;                         // this lane's input column
+    const uint32_t *const col = reinterpret_cast<const uint32_t *>(smem + (col_abs - smem_abs));
     const uint32_t stage0_abs = blk_abs + kInRows * kWarpRowBytes;
-    uint8_t *const stage0 = blk + kInRows * kWarpRowBytes;
     uint32_t store_pending = 0;   // bit b: a TMA store may still be reading staging buffer b
     bool prev_valid = false;
     uint32_t prev_cnt = 0, prev_incl = 0;
+    // warps whose 32 chunks are all complete, with their look-ahead units, and that do not hold chunk 0
+    const uint64_t chunks_seg = p.n_segments / SEGS;
+    const uint64_t chunks_unit = p.n_units >= 2 ? (p.n_units - 2) / (4u * SEGS) : 0;
+    const uint64_t fast_chunks = chunks_seg < chunks_unit ? chunks_seg : chunks_unit;
 
     // Inputs of the NEXT tile are prefetched into registers while the previous tile is compacted and flushed, so
     // that the DRAM latency of the unit loads is off the critical path of a step.
@@ -207,8 +234,7 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
         if (tile >= p.n_tiles) return;
         const uint64_t cw = (tile * nw + warp) * 32u;   // first chunk of this warp
         const uint64_t g0 = (cw + lane) * SEGS;
-        // interior warp (uniform test): every lane has a full chunk, the look-ahead units exist, chunk 0 is elsewhere
-        if (cw != 0 && (cw + 32u) * SEGS <= p.n_segments && (cw + 32u) * SEGS * 4u + 2u <= p.n_units) {
+        if (cw != 0 && cw + 32u <= fast_chunks) {       // interior warp (uniform test)
             const uint32_t *u = p.units + g0 * 4;
 #pragma unroll
             for (int q = 0; q < SEGS; ++q) pf_w[q] = __ldg(reinterpret_cast<const uint4 *>(u) + q);
@@ -216,7 +242,7 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
             const uint64_t j1 = g0 + SEGS - 1;
             pf_gw0 = __ldg(p.gap_words + ((g0 - 1) >> 3));
             pf_gw1 = __ldg(p.gap_words + (j1 >> 3));
-            pf_sh = (4u * (uint32_t)((g0 - 1) & 7)) | (4u * (uint32_t)(j1 & 7)) << 8;
+            pf_sh = (4u * ((uint32_t)(g0 - 1) & 7u)) | (4u * ((uint32_t)j1 & 7u)) << 8;
             pf_bits = SEGS * kSegmentBits;
             return;
         }
@@ -276,13 +302,13 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
                 const uint32_t pf_stop = pf_bits + ((pf_gw1 >> (pf_sh >> 8)) & 15u);
 #pragma unroll
                 for (int q = 0; q < SEGS; ++q) {
-                    col[(4 * q + 0) * 32] = pf_w[q].x;
-                    col[(4 * q + 1) * 32] = pf_w[q].y;
-                    col[(4 * q + 2) * 32] = pf_w[q].z;
-                    col[(4 * q + 3) * 32] = pf_w[q].w;
+                    smem_st_u32(col_abs + (4 * q + 0) * kWarpRowBytes, pf_w[q].x, nullptr);
+                    smem_st_u32(col_abs + (4 * q + 1) * kWarpRowBytes, pf_w[q].y, nullptr);
+                    smem_st_u32(col_abs + (4 * q + 2) * kWarpRowBytes, pf_w[q].z, nullptr);
+                    smem_st_u32(col_abs + (4 * q + 3) * kWarpRowBytes, pf_w[q].w, nullptr);
                 }
-                col[(4 * SEGS + 0) * 32] = pf_la.x;
-                col[(4 * SEGS + 1) * 32] = pf_la.y;
+                smem_st_u32(col_abs + (4 * SEGS + 0) * kWarpRowBytes, pf_la.x, nullptr);
+                smem_st_u32(col_abs + (4 * SEGS + 1) * kWarpRowBytes, pf_la.y, nullptr);
                 cnt = decode_chunk<32, LONG>(col, pf_entry, pf_stop, T, stage0_abs + b * stage_bytes + lane * 4u, nullptr);
             }
             // ---------------- warp-wide inclusive scan of the counts ----------------
@@ -310,58 +336,54 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
         if (k == 0) {
             while (ld_acquire_cta_u32(&s_t1_ready) == 0) __nanosleep(100);   // the scan warp's second ticket
         }
-        if (prev_valid) {
-            // wait for the scan warp's prefix of tile k-1 (computed while we decoded tile k)
-            mbar_wait(&s_ready[b ^ 1u], ((k - 1u) >> 1) & 1u);
-        }
-        if (valid) prefetch(s_tileid[(k + 1u) % 3u]);   // published with s_t1_ready / s_ready above
+        // the scan warp's prefix of tile k-1 (computed while this warp decoded tile k); its arrival also publishes the
+        // ticket of step k+1 (k == 0: s_t1_ready above)
+        if (prev_valid) mbar_wait_suspended(&s_ready[b ^ 1u], ((k - 1u) >> 1) & 1u);
+        if (valid) prefetch(s_tileid[(k + 1u) % 3u]);
         if (prev_valid) {
             // ---------------- finish tile k-1: compact this warp's symbols in place and flush them ----------------
             const uint32_t pb = b ^ 1u;
-            const uint64_t base = s_base[pb];
             const uint32_t woff = s_wtot[pb][warp];                            // this warp's offset in the tile
+            const uint32_t lim = s_lim[pb];                                    // output capacity left at the tile start
+            uint8_t *const gp = reinterpret_cast<uint8_t *>((uintptr_t)s_gbase[pb]) + woff;   // the warp's destination
             const uint32_t wtot = __shfl_sync(0xffffffffu, prev_incl, 31);     // this warp's symbols
             const uint32_t excl_l = prev_incl - prev_cnt;
-            const uint64_t wbase = base + woff;                                // this warp's offset in the output
             // clamp to n_symbols (pad bits decode to garbage: the reference clamps with out_pos < next_out_pos,
             // cuhd_gpu_decoder.cu:101-105)
-            const uint64_t lim = wbase >= n_symbols ? 0 : n_symbols - wbase;
-            const uint32_t total = wtot < lim ? wtot : (uint32_t)lim;
+            const uint32_t room = lim > woff ? lim - woff : 0u;
+            const uint32_t total = wtot < room ? wtot : room;
             uint32_t c = prev_cnt;
-            if (excl_l >= total) c = 0;
-            else if (excl_l + c > total) c = total - excl_l;
-            uint8_t *gp = out + wbase;
+            if (excl_l + c > total) c = excl_l >= total ? 0u : total - excl_l;
             const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gp) & 15u);
-            uint8_t *sblk = stage0 + pb * stage_bytes;
+            const uint32_t sblk = stage0_abs + pb * stage_bytes;
             const uint32_t rows_max = warp_max_u32((prev_cnt + 3u) >> 2);
             uint32_t w[RCAP + 2];
 #pragma unroll
             for (int i = 0; i < RCAP + 2; ++i) w[i] = 0;
-            column_read<RCAP>(reinterpret_cast<const uint32_t *>(sblk) + lane, rows_max, w);
+            column_read<RCAP>(sblk + lane * 4u, rows_max, w, nullptr);
             __syncwarp();
-            column_write<RCAP>(w, c, sblk, phase + excl_l, rows_max);
+            const uint32_t D = sblk + phase + excl_l;
+            column_write<RCAP>(w, c, D, rows_max, nullptr);
             __syncwarp();
-            column_write_head(w[0], c, sblk, phase + excl_l);
+            column_write_head(w[0], c, D, nullptr);
             fence_proxy_async_smem();
             __syncwarp();
             // flush: the warp's span is contiguous in the block and in the output, and both have the same 16-byte
             // phase -> one TMA bulk store for the aligned body, lanes 0-15 / 16-31 for head / tail bytes
-            const uint8_t *sp = sblk + phase;
+            const uint32_t sp = sblk + phase;
             uint32_t head = (16u - phase) & 15u;
             if (head > total) head = total;
             const uint32_t body = (total - head) & ~15u;
             const uint32_t tail = total - head - body;
-            if (lane == 0 && body) {
-                tma_bulk_store(gp + head, sp + head, body);
-                tma_bulk_commit();
+            if (body) {   // (warp-uniform)
+                if (lane == 0) {
+                    tma_bulk_store_s(gp + head, sp + head, body);
+                    tma_bulk_commit();
+                }
+                store_pending |= 1u << pb;
             }
-            if (body) store_pending |= 1u << pb;   // (warp-uniform)
-            if (lane < 16) {
-                if (lane < head) gp[lane] = sp[lane];
-            } else {
-                const uint32_t i = lane - 16;
-                if (i < tail) gp[head + body + i] = sp[head + body + i];
-            }
+            const uint32_t hb = lane < 16 ? lane : head + body + lane - 16u;   // byte of the span this lane may copy
+            if (lane < 16 ? lane < head : lane - 16u < tail) gp[hb] = (uint8_t)smem_ld_u8(sp + hb);
         }
         if (!valid) break;
         prev_valid = true;

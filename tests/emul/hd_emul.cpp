@@ -203,10 +203,10 @@ static int64_t emul_decode_tiles(HostTables &h, const uint32_t *units, uint64_t 
             if (excl[l] >= total) c[l] = 0;
             else if (excl[l] + c[l] > total) c[l] = total - excl[l];
             for (int i = 0; i < RCAP + 2; ++i) w[l][i] = 0;
-            column_read<RCAP>(reinterpret_cast<const uint32_t *>(sblk) + l, rows_max, w[l]);
+            column_read<RCAP>(stage_off + l * 4u, rows_max, w[l], arena.data());
         }
-        for (uint32_t l = 0; l < 32; ++l) column_write<RCAP>(w[l], c[l], sblk, phase + excl[l], rows_max);
-        for (uint32_t l = 0; l < 32; ++l) column_write_head(w[l][0], c[l], sblk, phase + excl[l]);
+        for (uint32_t l = 0; l < 32; ++l) column_write<RCAP>(w[l], c[l], stage_off + phase + excl[l], rows_max, arena.data());
+        for (uint32_t l = 0; l < 32; ++l) column_write_head(w[l][0], c[l], stage_off + phase + excl[l], arena.data());
         std::memcpy(out + base, sblk + phase, total);
         base += wtot;
     }
