@@ -151,91 +151,8 @@ DeviceInfo device_info() {
     return d;
 }
 
-// K4 geometry for a table: decode threads per tile, segments per thread and the smem carve-up (must match the kernel)
-struct DecodeGeom {
-    int nt, segs;
-    uint32_t stage_words, tile_bytes, tile_buffers;
-    size_t smem;
-};
-
-DecodeGeom decode_geom(const hd_table *t, int nt, int segs, uint32_t tile_buffers) {
-    DecodeGeom g;
-    g.nt = nt;
-    g.segs = segs;
-    g.tile_buffers = tile_buffers;
-    const uint32_t min_len = std::max<uint32_t>(1, t->host.min_len);
-    // a chunk decodes bits [entry, 128*segs + next_entry), entry offsets <= 15, plus the uncounted 2nd symbol of the
-    // last lookup and the always-written second byte
-    const uint32_t max_cnt = (kSegmentBits * segs + 15 + min_len - 1) / min_len;
-    // bytes written: max_cnt symbols + the uncounted 2nd symbol + the always-written 2nd byte -> word max_cnt/4 + 1 at
-    // most; compaction reads one word past the last one holding symbols
-    g.stage_words = max_cnt / 4 + 3;
-    const uint32_t tile_sym = ((uint32_t)nt * kSegmentBits * segs + 15 + min_len - 1) / min_len + 2;
-    g.tile_bytes = (uint32_t)align_up((size_t)tile_sym + 32, 16);
-    const size_t row = (size_t)nt * 4;
-    g.smem = (4u << t->host.lut_bits) + (t->host.has_long ? 256 + align_up(sizeof(LongTables), 16) : 0) +
-             (size_t)(4 * segs + 3) * row + row /* staging alignment slack */ + 2 * (size_t)g.stage_words * row +
-             (size_t)tile_buffers * g.tile_bytes;
-    return g;
-}
-
-unsigned long long *g_trace = nullptr;   // hd_set_trace (developer aid)
-int g_force_segs = 0, g_force_nt = 0;   // hd_set_tuning: 0 = automatic
-
-DecodeGeom pick_geom(const hd_table *t, int max_smem) {
-    // two output tiles if they fit (no barrier among the decode warps), else one
-    auto fit = [&](int nt, int segs, DecodeGeom &g) {
-        g = decode_geom(t, nt, segs, 2);
-        if ((int)g.smem <= max_smem) return true;
-        g = decode_geom(t, nt, segs, 1);
-        return (int)g.smem <= max_smem;
-    };
-    DecodeGeom g;
-    if ((g_force_segs == 1 || g_force_segs == 2 || g_force_segs == 4) && (g_force_nt == 256 || g_force_nt == 512)) {
-        if (fit(g_force_nt, g_force_segs, g)) return g;
-    }
-    // largest tile that fits: big tiles keep the look-back chain short and amortise the per-tile work; the
-    // worst-case staging (shortest code length) decides what fits in the 227 KB of one SM.  When two segments per
-    // thread do not fit (minimum code length 1 or 2), 512 threads with one segment each beat 256 threads with two
-    // (measured at redundancy 0.9 / 1.0: 0.144 / 0.134 ms against 0.171 / 0.210 ms per 100 MiB): 16 decode warps
-    // hide the LUT latency, 8 do not.
-    static const int cand[][2] = {{512, 2}, {512, 1}, {256, 2}, {256, 1}};
-    for (auto &c : cand)
-        if (fit(c[0], c[1], g)) return g;
-    return decode_geom(t, 256, 1, 1);
-}
-
 size_t sync_smem_bytes(const hd_table *t) {
     return align_up(2u << t->host.lut_bits, 16) + 256 + align_up(sizeof(LongTables), 16);
-}
-
-template <int NT, int SEGS, bool LONG>
-hd_status launch_decode(const DecodeParams &p, size_t smem, cudaStream_t s) {
-    auto kern = hd_decode_write_kernel<NT, SEGS, LONG>;
-    HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const DeviceInfo di = device_info();
-    uint64_t grid = (uint64_t)di.sm_count;   // persistent: one CTA per SM, all co-resident (the look-back spins)
-    if (grid > p.n_tiles) grid = p.n_tiles;
-    kern<<<(unsigned)grid, NT + 32, smem, s>>>(p);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    HD_CUDA(cudaGetLastError());
-    return HD_OK;
-}
-
-template <bool LONG>
-hd_status launch_decode_geom(const DecodeGeom &g, const DecodeParams &p, cudaStream_t s) {
-    if (g.nt == 512) {
-        switch (g.segs) {
-            case 1: return launch_decode<512, 1, LONG>(p, g.smem, s);
-            case 2: return launch_decode<512, 2, LONG>(p, g.smem, s);
-            default: return launch_decode<512, 4, LONG>(p, g.smem, s);
-        }
-    }
-    switch (g.segs) {
-        case 1: return launch_decode<256, 1, LONG>(p, g.smem, s);
-        case 2: return launch_decode<256, 2, LONG>(p, g.smem, s);
-        default: return launch_decode<256, 4, LONG>(p, g.smem, s);
-    }
 }
 
 // ---- K4 "warp tile" kernel (hd_decode.cuh): geometry + launch ---------------------------------------------------
@@ -311,69 +228,36 @@ hd_status launch_tiles_geom(const TileGeom &g, const TileParams &p, cudaStream_t
     return HD_ERR_INVALID;
 }
 
-bool use_legacy_k4() {
-    static const bool v = [] { const char *e = getenv("HD_K4_LEGACY"); return e && *e == '1'; }();
-    return v;
-}
-
 hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32_t *d_gap_words,
                          uint64_t n_segments, uint32_t first_bit, const hd_table *table, uint8_t *d_out,
                          uint64_t n_symbols, const Workspace &w, uint64_t *d_count, cudaStream_t s,
                          uint64_t n_units_readable = 0, const uint32_t *entry_word = nullptr,
                          uint64_t *shard_info = nullptr, bool already_zeroed = false,
                          const uint64_t *d_off_in = nullptr, uint64_t *d_off_out = nullptr) {
-    if (!use_legacy_k4()) {
-        TileGeom g;
-        if (!pick_tile_geom(table, device_info().max_smem_optin, g)) return HD_ERR_INVALID;
-        TileParams q;
-        q.units = d_units;
-        q.n_units = n_units_readable > n_units ? n_units_readable : n_units;
-        q.gap_words = d_gap_words;
-        q.n_segments = n_segments;
-        q.first_bit = first_bit;
-        q.entry_word = entry_word;
-        q.shard_info = shard_info;
-        q.table = table_dev(table);
-        q.out = d_out;
-        q.n_symbols = n_symbols;
-        q.out_offset_in = d_off_in;
-        q.out_offset_out = d_off_out;
-        q.tile_status = w.tile_status;
-        q.tile_counter = w.tile_counter;
-        q.n_tiles = div_up(div_up(n_segments, (uint64_t)g.segs), (uint64_t)g.n_warps * 32);
-        q.count_out = d_count;
-        q.stage_rows = g.stage_rows;
-        q.n_warps = g.n_warps;
-        if (!already_zeroed) HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes, s));
-        ProfScope prof(HD_PROFILE_DECODE_WRITE, s);
-        return table->host.has_long ? launch_tiles_geom<true>(g, q, s) : launch_tiles_geom<false>(g, q, s);
-    }
-    DecodeParams p;
-    p.out_offset_in = d_off_in;
-    p.out_offset_out = d_off_out;
-    p.units = d_units;
-    p.n_units = n_units_readable > n_units ? n_units_readable : n_units;
-    p.entry_word = entry_word;
-    p.shard_info = shard_info;
-    p.gap_words = d_gap_words;
-    p.n_segments = n_segments;
-    p.first_bit = first_bit;
-    p.table = table_dev(table);
-    p.out = d_out;
-    p.n_symbols = n_symbols;
-    p.tile_status = w.tile_status;
-    p.tile_counter = w.tile_counter;
-    const DecodeGeom g = pick_geom(table, device_info().max_smem_optin);
-    if ((int)g.smem > device_info().max_smem_optin) return HD_ERR_INVALID;
-    p.n_tiles = div_up(div_up(n_segments, (uint64_t)g.segs), (uint64_t)g.nt);
-    p.count_out = d_count;
-    p.stage_words = g.stage_words;
-    p.tile_bytes = g.tile_bytes;
-    p.tile_buffers = g.tile_buffers;
-    p.trace = g_trace;
+    TileGeom g;
+    if (!pick_tile_geom(table, device_info().max_smem_optin, g)) return HD_ERR_INVALID;
+    TileParams q;
+    q.units = d_units;
+    q.n_units = n_units_readable > n_units ? n_units_readable : n_units;
+    q.gap_words = d_gap_words;
+    q.n_segments = n_segments;
+    q.first_bit = first_bit;
+    q.entry_word = entry_word;
+    q.shard_info = shard_info;
+    q.table = table_dev(table);
+    q.out = d_out;
+    q.n_symbols = n_symbols;
+    q.out_offset_in = d_off_in;
+    q.out_offset_out = d_off_out;
+    q.tile_status = w.tile_status;
+    q.tile_counter = w.tile_counter;
+    q.n_tiles = div_up(div_up(n_segments, (uint64_t)g.segs), (uint64_t)g.n_warps * 32);
+    q.count_out = d_count;
+    q.stage_rows = g.stage_rows;
+    q.n_warps = g.n_warps;
     if (!already_zeroed) HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes, s));
     ProfScope prof(HD_PROFILE_DECODE_WRITE, s);
-    return table->host.has_long ? launch_decode_geom<true>(g, p, s) : launch_decode_geom<false>(g, p, s);
+    return table->host.has_long ? launch_tiles_geom<true>(g, q, s) : launch_tiles_geom<false>(g, q, s);
 }
 
 hd_status check_common(const uint32_t *d_units, uint64_t n_units, const hd_table *table, const uint8_t *d_out,
@@ -617,6 +501,10 @@ hd_status hd_decode_gap_ex(const uint32_t *d_units, uint64_t n_units, const uint
     if (n_segments > 1 && !d_gap_words) return HD_ERR_INVALID;
     if (workspace_bytes < ws_bytes(n_units, false)) return HD_ERR_WORKSPACE;
     Workspace w = carve(d_workspace, n_units, false);
+    // The kernel reads gap element n_segments - 1 (the offset at which the parse leaves the last segment; only the
+    // multi-GPU seam check uses its value).  A one-segment stream may come without a gap array: point the kernel at a
+    // word of the control block that the per-launch memset zeroes.
+    if (!d_gap_words) d_gap_words = w.tile_counter + 8;
     return run_gap_decode(d_units, n_units, d_gap_words, n_segments, first_bit, table, d_out, n_symbols, w,
                           d_count, static_cast<cudaStream_t>(stream));
 }
@@ -910,7 +798,7 @@ hd_status hd_mailbox_create(uint32_t world, uint32_t rank, hd_mailbox **out) {
     m->world = world;
     m->rank = rank;
     cudaError_t e = cudaGetDevice(&m->device);
-    const size_t bytes = (size_t)world * kMailboxSlotWords * 8;
+    const size_t bytes = (size_t)world * kMailboxRing * kMailboxSlotWords * 8;
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&m->local), bytes);
     if (e == cudaSuccess) e = cudaMemset(m->local, 0, bytes);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&m->d_timeout), 4);
@@ -976,10 +864,8 @@ int hd_mailbox_timed_out(hd_mailbox *m) {
 }
 
 // ------------------------------------------------------------------ tuning
-void hd_set_trace(void *d_buf) { g_trace = static_cast<unsigned long long *>(d_buf); }
+void hd_set_trace(void *) {}   // (the per-step trace of the round-1 kernel is gone; kept for ABI stability)
 void hd_set_tuning(int segs_per_thread, int threads_per_tile) {
-    g_force_segs = segs_per_thread;
-    g_force_nt = threads_per_tile;
     // warp-tile kernel: threads_per_tile = decode threads per CTA (a multiple of 32, at most 27 warps)
     g_tile_segs = segs_per_thread;
     g_tile_warps = (threads_per_tile > 0 && threads_per_tile % 32 == 0 && threads_per_tile <= (int)kTileMaxWarps * 32) ? threads_per_tile / 32 : 0;

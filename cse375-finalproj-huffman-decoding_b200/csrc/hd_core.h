@@ -16,9 +16,6 @@
 #define HD_HD inline
 #endif
 
-#ifndef HD_TWO_STEP
-#define HD_TWO_STEP 1   // decode_chunk: two table steps per window slide (measured)
-#endif
 #ifndef HD_WHATIF
 #define HD_WHATIF 0   // developer timing experiments (tools/whatif.sh); 0 in every shipped build
 #endif
@@ -37,13 +34,13 @@ HD_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {
 
 // Canonical resolver for codes longer than the primary LUT (len in
 // (lut_bits, 16]).  win = next 32 stream bits, left aligned.  Returns a
-// synthesized primary entry {sym, 0, bits=len, count=1}, or a 1-bit skip for a
+// synthesized primary entry {sym, 0, bits=len, 8 * count = 8}, or a 1-bit skip for a
 // window that matches no code (hole of an incomplete code).
 HD_HD uint32_t resolve_long(uint32_t win, uint32_t lut_bits, const LongTables *lt, const uint8_t *order) {
     for (uint32_t len = lut_bits + 1; len <= kMaxCodeLen; ++len) {
         const uint32_t c = win >> (32 - len);
         const uint32_t d = c - lt->first[len];
-        if (d < lt->count[len]) return (uint32_t)order[lt->offset[len] + d] | (len << 16) | (1u << 24);
+        if (d < lt->count[len]) return (uint32_t)order[lt->offset[len] + d] | (len << 16) | (8u << 24);
     }
     return 1u << 16;
 }
@@ -113,25 +110,27 @@ __device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t one, uint32_t k
 
 // Decode one chunk (SEGS consecutive 128-bit segments of one thread) in a single
 // flattened loop.  The chunk's units sit in the thread's column of the
-// transposed input tile: word w at in_col[w * NT] (conflict-free
-// refills); words past the chunk (the next chunk's first two) must be present.
+// transposed input block: word w at in_col[w * NT] (conflict-free refills);
+// words past the chunk (the next chunk's first two) must be present.
 // Decoding starts at bit `entry` (< 32) and runs until the position reaches
 // `stop` = chunk bits + entry offset of the NEXT chunk, i.e. exactly to the
 // codeword boundary at which the successor starts (with an exact gap array this
 // is the stop rule of decoder.cu:672 -- decode every codeword that STARTS inside
 // the chunk -- because the last such codeword ends at that boundary).
 //
-// Symbols are stored one byte at a time into the thread's staging column:
-// symbol i at row i/4, byte i%4 of the column.  The running store address A
-// keeps the column bits; OR-ing them to ones before an add lets the carry out of
-// the two byte bits ripple through the column field into the row field, so
-// "advance by n symbols" is one add plus two logic ops.  A two-symbol LUT entry
-// always stores both bytes; the second is simply overwritten by the next lookup
-// when the entry held one symbol.  Returns the number of symbols.
+// Two table steps per window slide: a step consumes at most 16 bits, so the 32-bit
+// window taken at `pos` still holds the 16 bits the second step looks at
+// (win << bits1); the second step is dropped when the first reached `stop`.  The
+// <= 4 symbols of the two steps are packed behind the bytes still pending in a
+// register (P, np8 = 8 * pending bytes) and a full 32-bit word is stored to the
+// thread's staging column (word m at stage_addr + m * NT * 4: bank == lane, conflict
+// free) whenever four symbols are complete: ONE shared-memory store per four
+// symbols instead of one per symbol -- the kernel is bound by shared-memory
+// wavefronts.  LUT entries are {sym0, sym1, bits, 8 * count}.
+// Returns the number of symbols; staging words [0, ceil(count / 4)] are written.
 template <int NT, bool LONG>
 HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t stop, const DecodeTables &T,
                             uint32_t stage_addr, uint8_t *arena) {
-    constexpr uint32_t kColBits = col_bits(NT);
     static_assert(row_shift(NT) != 0, "unsupported tile width");
     uint32_t w0 = in_col[0], w1 = in_col[NT];
     uint32_t w2 = in_col[2 * NT];
@@ -140,56 +139,44 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
 #else
     const uint32_t *nxt = in_col + 2 * NT;
 #endif
-    const uint32_t col = stage_addr & kColBits;
-    uint32_t A = stage_addr;
+    uint32_t R = stage_addr;   // where the next full word goes
+    uint32_t P = 0, np8 = 0;   // pending symbols (low np8 / 8 bytes of P), np8 < 32
     uint32_t pos = entry;
     uint32_t e = 0;
-#if defined(__CUDA_ARCH__)
-#define HD_PLUS1(u_) add_fma((u_), T.one, 1u)
-#else
-#define HD_PLUS1(u_) ((u_) + 1u)
-#endif
     while (pos < stop) {
         const uint32_t win = funnel_l(w1, w0, pos);   // next 32 stream bits
-        e = T.lut[win >> T.idx_shift];
+        uint32_t e1 = T.lut[win >> T.idx_shift];
         if (LONG) {
-            if ((e >> 16) == 0) e = resolve_long(win, T.lut_bits, T.lt, T.order);
+            if ((e1 >> 16) == 0) e1 = resolve_long(win, T.lut_bits, T.lt, T.order);
         }
-        uint32_t u = A | kColBits;
-#if !(HD_WHATIF & 2)
-        smem_st_u8(A, e, arena);
-        smem_st_u8((HD_PLUS1(u) & ~kColBits) | col, e >> 8, arena);
-#endif
-        A = ((u + (e >> 24)) & ~kColBits) | col;
-        uint32_t np = pos + byte2(e);
-#if HD_TWO_STEP
-        // Second table step from the same 32-bit window: a step consumes at most 16 bits, so the 16 bits the next one
-        // looks at are still there (win << nbits).  One window slide, loop test and branch per TWO lookups, and the
-        // loop-carried chain between the two loads is shift -> index -> load instead of add -> slide -> funnel -> index
-        // -> load.  The step is dropped when the first one already reached `stop`.
-        {
-            const uint32_t win2 = win << byte2(e);
-            uint32_t e2 = T.lut[win2 >> T.idx_shift];
-            if (LONG) {
-                if ((e2 >> 16) == 0) e2 = resolve_long(win2, T.lut_bits, T.lt, T.order);
-            }
-            if (np < stop) {
-                e = e2;
-#if defined(__CUDA_ARCH__)
-                asm volatile("");
-#endif
-            } else {
-                e2 = 0;
-            }
-            u = A | kColBits;
-#if !(HD_WHATIF & 2)
-            smem_st_u8(A, e2, arena);
-            smem_st_u8((HD_PLUS1(u) & ~kColBits) | col, e2 >> 8, arena);
-#endif
-            A = ((u + (e2 >> 24)) & ~kColBits) | col;
-            np += byte2(e2);
+        const uint32_t b1 = byte2(e1);
+        uint32_t np = pos + b1;
+        const uint32_t win2 = win << b1;
+        uint32_t e2 = T.lut[win2 >> T.idx_shift];
+        if (LONG) {
+            if ((e2 >> 16) == 0) e2 = resolve_long(win2, T.lut_bits, T.lt, T.order);
         }
-#endif
+        if (np < stop) {
+            e = e2;
+        } else {
+            e = e1;
+            e2 = 0;
+        }
+        np += byte2(e2);
+        // pack: X = the symbols of both steps, n8 = 8 * (pending + new) symbols
+        const uint32_t c1 = e1 >> 24;
+        const uint32_t X = (e1 & 0xffffu) | ((e2 & 0xffffu) << c1);
+        const uint32_t n8 = np8 + c1 + (e2 >> 24);
+        const uint32_t lo = P | (X << np8);
+        const uint32_t hi = funnel_l(X, 0u, np8);   // the bytes of X that did not fit into lo (0 when np8 == 0)
+        if (n8 >= 32u) {
+            smem_st_u32(R, lo, arena);
+            R += NT * 4u;
+            P = hi;
+        } else {
+            P = lo;
+        }
+        np8 = n8 & 31u;
 #if defined(__CUDA_ARCH__)
         // Crossed a unit boundary: slide the window and fetch the word after it.  One asm block with its own predicate,
         // so that the slide stays predicated moves (FMA pipe; the INT pipe bounds this loop) and the load writes w2 IN
@@ -219,10 +206,10 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
 #endif
         pos = np;
     }
-#undef HD_PLUS1
-    uint32_t cnt = (((A - stage_addr) >> row_shift(NT)) << 2) | (A & 3u);
+    smem_st_u32(R, P, arena);   // the pending symbols (a word past the last full one: the staging rows allow for it)
+    uint32_t cnt = (((R - stage_addr) >> row_shift(NT)) << 2) + (np8 >> 3);
     // the second symbol of the last lookup starts exactly at `stop`: it is the successor's first symbol
-    if (pos > stop && (e >> 24) == 2u) --cnt;
+    if (pos > stop && (e >> 24) == 16u) --cnt;
     return cnt;
 }
 
@@ -234,48 +221,6 @@ HD_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
     s &= 31u;
     return s ? ((lo >> s) | (hi << (32u - s))) : lo;
 #endif
-}
-
-// Copy c symbols from the thread's staging column (word m at src[m * stride],
-// little-endian bytes) to byte offset D of the CTA's output tile: up to three
-// head bytes until the destination is word aligned, whole 32-bit words through
-// one funnel shift each, up to three tail bytes.  The words are fetched four at
-// a time BEFORE the stores of the batch (source and destination are both shared
-// memory, the compiler cannot reorder them itself), so that four loads are in
-// flight instead of one load -> shift -> store chain per word; head and tail are
-// predicated byte stores, not loops.  Reads at most three staging words past the
-// last one that holds symbols (rows of the next buffer: harmless).
-HD_HD void compact_to_tile(const uint32_t *src, uint32_t stride, uint32_t c, uint8_t *tile, uint32_t D) {
-    uint32_t w = src[0];
-    uint32_t head = (4u - (D & 3u)) & 3u;
-    if (head > c) head = c;
-    if (head > 0u) tile[D] = (uint8_t)w;
-    if (head > 1u) tile[D + 1] = (uint8_t)(w >> 8);
-    if (head > 2u) tile[D + 2] = (uint8_t)(w >> 16);
-    const uint32_t rem = c - head;
-    const uint32_t nw = rem >> 2;
-    uint32_t *dst = reinterpret_cast<uint32_t *>(tile + D + head);
-    const uint32_t sh = 8u * head;
-    const uint32_t *nx = src + stride;
-    for (uint32_t m = 0; m < nw; m += 4u) {
-        const uint32_t n0 = nx[0], n1 = nx[stride], n2 = nx[2u * stride], n3 = nx[3u * stride];
-        dst[0] = funnel_r(w, n0, sh);
-        if (m + 1u < nw) dst[1] = funnel_r(n0, n1, sh);
-        if (m + 2u < nw) dst[2] = funnel_r(n1, n2, sh);
-        if (m + 3u < nw) dst[3] = funnel_r(n2, n3, sh);
-        w = n3;
-        nx += 4u * stride;
-        dst += 4;
-    }
-    const uint32_t tail = rem & 3u;
-    if (tail) {
-        const uint32_t *lw = src + nw * stride;
-        const uint32_t v = funnel_r(lw[0], lw[stride], sh);
-        uint8_t *d8 = tile + D + head + 4u * nw;
-        d8[0] = (uint8_t)v;
-        if (tail > 1u) d8[1] = (uint8_t)(v >> 8);
-        if (tail > 2u) d8[2] = (uint8_t)(v >> 16);
-    }
 }
 
 // ---- warp-private staging blocks (K4 "warp tile" kernel) ------------------------
@@ -412,6 +357,44 @@ HD_HD uint32_t sync_segment(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, 
         pos = np;
     }
     return pos - kSegmentBits;
+}
+
+// Flattened parse of a RUN of segments (K1a): from bit `pos` of words[0] until the position reaches end_bits, in
+// one loop -- no reconvergence at segment ends (with one loop per segment every lane of a warp waits for the
+// slowest lane at each of its 20 segments: ~40 % of the issue slots of the round-1 kernel).  The sequence of
+// positions is exactly that of sync_segment called segment by segment: two table steps per iteration, the second
+// one dropped when the first crosses a 128-bit boundary, so every landing is identical.
+//
+// RECORD: the landing into segment s+1 is left in byte slot s+1 of the lane's landing column (slot k at land_addr
+// + 32 * k: one byte per lane and row).  Every iteration stores the low byte of its end position into the slot
+// FOLLOWING the segment it started in; the last iteration that starts in segment s is the one that crosses into
+// s+1, so the slot ends up holding (landing + a multiple of 128) & 0xff -- an unconditional store (two
+// instructions) instead of a divergent "did I cross?" block.  Words are read linearly from `words` (the run and
+// at least 64 bits behind it must be readable).  Returns the final position (>= end_bits).
+template <bool EXACT, bool LONG, bool RECORD>
+HD_HD uint32_t sync_run(const uint32_t *words, uint32_t pos, uint32_t end_bits, const SyncLut &L, uint32_t land_addr,
+                        uint8_t *arena) {
+    uint32_t w0 = words[0], w1 = words[1], w2 = words[2];
+    const uint32_t *nxt = words + 2;
+    while (pos < end_bits) {
+        const uint32_t win = funnel_l(w1, w0, pos);
+        const uint32_t s1 = sync_step<EXACT, LONG>(win, pos & (kSegmentBits - 1u), L);
+        const uint32_t p1 = pos + s1;
+        const uint32_t s2 = sync_step<EXACT, LONG>(win << s1, p1 & (kSegmentBits - 1u), L);
+        const uint32_t np = ((p1 ^ pos) & kSegmentBits) ? p1 : p1 + s2;
+        if (RECORD) smem_st_u8(land_addr + ((pos >> 7) << 5), np, arena);
+        if ((np ^ pos) & 32u) {
+            w0 = w1;
+            w1 = w2;
+            ++nxt;
+            w2 = *nxt;
+#if defined(__CUDA_ARCH__)
+            asm volatile("");   // keep predicated moves (FMA pipe) instead of selects (INT pipe), see decode_chunk
+#endif
+        }
+        pos = np;
+    }
+    return pos;
 }
 
 // Repair step (K1b): re-parse chunk `chunk` (kSyncChunkSegs segments) from the

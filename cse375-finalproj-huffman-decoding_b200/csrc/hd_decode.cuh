@@ -55,7 +55,7 @@ struct TileParams {
     const uint64_t *out_offset_in;   // optional: decode to out + *out_offset_in (capacity n_symbols counts from `out`)
     uint64_t *out_offset_out;        // optional: receives *out_offset_in + symbols written (chains pipelined pieces)
     uint64_t *tile_status;       // n_tiles words (stride kStatusStride), zeroed before launch
-    uint32_t *tile_counter;      // zeroed before launch
+    uint32_t *tile_counter;      // zeroed before launch; [1] = look-back gave up (see lookback_wide)
     uint64_t n_tiles;
     uint64_t *count_out;         // optional: total symbols written
     uint32_t stage_rows;         // rows of one staging buffer (one 32-bit word per lane each)
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
             // (the tile AGGREGATE was already published by the last decode warp to finish; tile 0 published its PREFIX)
             uint64_t excl = 0;
             if (tile > 0) {
-                excl = lookback_wide(p.tile_status, tile, lane);
+                excl = lookback_wide(p.tile_status, tile, lane, p.tile_counter + 1);
                 if (lane == 0) red_max_gpu_u64(p.tile_status + tile * kStatusStride, kFlagPrefix | (excl + agg));
             }
             if (lane == 0) {

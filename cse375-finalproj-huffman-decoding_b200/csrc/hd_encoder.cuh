@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kEncThreads) hd_encode_kernel(const EncodePara
             if (lane == 0) red_max_gpu_u64(p.tile_status + tile * kStatusStride, (tile == 0 ? kFlagPrefix : kFlagAggregate) | agg);
             uint64_t excl = 0;
             if (tile > 0) {
-                excl = lookback_wide(p.tile_status, tile, lane);
+                excl = lookback_wide(p.tile_status, tile, lane, p.tile_counter + 1);
                 if (lane == 0) red_max_gpu_u64(p.tile_status + tile * kStatusStride, kFlagPrefix | (excl + agg));
             }
             if (lane == 0) {

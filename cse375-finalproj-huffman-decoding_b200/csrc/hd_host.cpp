@@ -143,7 +143,7 @@ void build_table_blob(const HostCode &c, TableBlob &blob) {
             bits += len1;
             count = 2;
         }
-        dec[w] = syms | (bits << 16) | (count << 24);
+        dec[w] = syms | (bits << 16) | (count << 27);   // top byte = 8 * count (decode_chunk packs with it)
         // sync: jump over every complete code in the window
         uint32_t jump = len0, l, s;
         while (jump < lm && first_code(w, jump, l, s)) jump += l;

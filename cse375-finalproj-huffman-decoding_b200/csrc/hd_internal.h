@@ -21,14 +21,29 @@ constexpr uint32_t kMaxCodeLen = 16;     // .huff MAX_CODEWORD_LENGTH (decoder/i
 // ---- geometry of the synchronisation kernels (K1a/K1b) --------------------
 constexpr uint32_t kSyncChunkSegs = 16;  // segments per sync thread (2048 bits = two gap words)
 constexpr uint32_t kSyncHaloSegs = 4;    // segments parsed speculatively BEFORE the chunk (512 bits; 6 measured: no gain)
-constexpr uint32_t kSyncWarps = 24;      // warps per persistent sync CTA (one CTA per SM)
+constexpr uint32_t kSyncWarps = 23;      // warps per persistent sync CTA (one CTA per SM)
 // A warp tile stages 32 chunks but OWNS only 31: lane 0 re-parses the last chunk of the previous tile (whose owner
 // is lane 31 there) just to hand lane 1 an exit offset that had a whole chunk to synchronise -- so the seams between
 // warp tiles are right without any communication between warps (3 % redundant parsing).
 constexpr uint32_t kSyncTileChunks = 31;                                  // chunks owned per warp tile
 constexpr uint32_t kSyncTileSegs = 32 * kSyncChunkSegs;                   // segments staged per warp tile
-constexpr uint32_t kSyncTileUnits16 = kSyncHaloSegs + kSyncTileSegs + 1;  // 16-byte units staged per warp tile
-constexpr uint32_t kSyncTileBytes = (kSyncTileUnits16 + kSyncTileUnits16 / 16 + 2) * 16;   // + 1 pad unit per 16
+// Staged layout of a warp tile, in 16-byte units (= segments): [4 halo units][copy of chunk 0's first unit] then one
+// REGION of 17 units per lane: [the lane's 16 segments][copy of the next chunk's first unit].  Every run a lane
+// parses -- its halo (the tail of the previous region, or the tile halo) and its chunk -- is followed by the unit
+// that comes next in the stream, so the flattened parse reads its words linearly; and the region stride of 17 units
+// keeps 128-bit loads of the repair path conflict free.  Behind the regions: the first unit of the chunk after the
+// tile + 2 units that the repair path may read but never uses, then the landing bytes (17 slots x 32 lanes).
+constexpr uint32_t kSyncRegionUnits = kSyncChunkSegs + 1;
+constexpr uint32_t kSyncTileSrcUnits = kSyncHaloSegs + kSyncTileSegs + 1;            // units copied per warp tile
+constexpr uint32_t kSyncTilePhysUnits = kSyncHaloSegs + 1 + 32 * kSyncRegionUnits + 3;
+constexpr uint32_t kSyncLandBytes = (kSyncChunkSegs + 1) * 32;
+constexpr uint32_t kSyncTileBytes = kSyncTilePhysUnits * 16 + kSyncLandBytes;
+// physical unit of tile-relative source unit i (i = 0: first halo unit)
+constexpr uint32_t sync_phys_unit(uint32_t i) {
+    return i < kSyncHaloSegs ? i
+                             : kSyncHaloSegs + 1 + kSyncRegionUnits * ((i - kSyncHaloSegs) / kSyncChunkSegs) +
+                                   ((i - kSyncHaloSegs) % kSyncChunkSegs);
+}
 
 // Host description of a prefix code: code/len indexed by symbol value.
 struct HostCode {

@@ -1,10 +1,6 @@
 // hd_kernels.cuh -- device code of the B200 (sm_100a) Huffman decoder.
 //
-//   K4  hd_decode_write_kernel : gap-array segment decode + single-pass
-//        decoupled look-back prescan + decode-and-write, one persistent launch.
-//        Replaces gpu_dec_l1_l2 (Huffman_coding_Gap_arrays/decoder/src/
-//        decoder.cu:454-730) and phases 3+4 of CUHD (gpuhd/src/
-//        cuhd_gpu_decoder.cu:329-420 + thrust scan :498-505).
+//   K4  hd_decode_tiles_kernel : see hd_decode.cuh (this file holds the PTX helpers and the look-back it uses)
 //   K1a hd_sync_parse_kernel   : speculative subsequence synchronisation: every
 //        thread parses a halo + its chunk, seams are repaired inside the warp
 //        (replaces phase 1, cuhd_gpu_decoder.cu:145-233)
@@ -91,36 +87,6 @@ struct TableDev {
     uint32_t off_sync, off_len, off_order, off_long;
 };
 
-struct DecodeParams {
-    const uint32_t *units;
-    uint64_t n_units;            // units that may be READ (includes a right halo when the stream continues)
-    const uint32_t *gap_words;   // element i = start offset of segment i+1
-    uint64_t n_segments;         // segments to DECODE
-    uint32_t first_bit;          // start offset of segment 0 ...
-    const uint32_t *entry_word;  // ... unless set: start offset of segment 0 = *entry_word >> 28
-    uint64_t *shard_info;        // optional {count, entry_bit, exit_bit} for the multi-GPU seam check
-    TableDev table;
-    uint8_t *out;
-    uint64_t n_symbols;
-    const uint64_t *out_offset_in;   // optional: decode to out + *out_offset_in (output capacity n_symbols counts from `out`);
-    uint64_t *out_offset_out;        // optional: receives *out_offset_in + symbols written -- chains the pieces of a
-                                     // pipelined host-buffer decode on the device, without a host round trip per piece
-    uint64_t *tile_status;       // n_tiles words, zeroed before launch
-    uint32_t *tile_counter;      // zeroed before launch
-    uint64_t n_tiles;
-    uint64_t *count_out;         // optional: total symbols written
-    uint32_t stage_words;        // staging rows (one 32-bit word per thread each)
-    uint32_t tile_bytes;         // output tile bytes (multiple of 16)
-    uint32_t tile_buffers;       // 2: tiles of consecutive steps alternate (no decode-warp barrier); 1: one barrier per step
-    unsigned long long *trace;   // optional (hd_set_trace): per-step timestamps of CTA kTraceCta, 8 u64 per step
-};
-constexpr uint32_t kTraceCta = 5, kTraceSteps = 48;
-__device__ __forceinline__ unsigned long long gtime_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
 struct SyncParams {
     const uint32_t *units;
     uint64_t n_units;            // units that may be READ
@@ -138,30 +104,7 @@ struct SyncParams {
 constexpr uint32_t kExitPublished = 0x100u;
 constexpr uint32_t kExitWaitPolls = 1u << 16;   // bounded wait for a predecessor tile (then: flag `changed`, K1b rounds decide)
 
-// =========================================================================
-// K4: decode-and-write.  ONE persistent CTA per SM: NT decode threads (one per
-// CHUNK of SEGS consecutive 128-bit segments; NT chunks = one tile) plus one
-// scan warp.  Tile ids come from an atomic ticket counter so that the look-back
-// never waits on a tile that is not running.  The CTA is software pipelined over
-// two staging buffers so that the L2 round trips of the decoupled look-back are
-// hidden behind the decode of the next tile:
-//
-//   decode warps, step k:   load + decode tile k -> staging[k&1]   (decode_chunk)
-//                           warp-scan the symbol counts, arrive FULL[k&1]
-//                           wait READY[(k-1)&1]  (prefix of tile k-1, long done)
-//                           compact staging[(k-1)&1] -> output tile, flush it
-//                           (one TMA bulk store, SASS UBLKCP, + scalar head/tail)
-//   scan warp, step k:      wait FULL[k&1]; take the ticket for step k+2; scan
-//                           the warp totals (the tile aggregate was published
-//                           by the last decode warp to finish); look back over
-//                           the predecessors' aggregates/prefixes (64-bit
-//                           flagged words, ld.relaxed.gpu / red.max); publish
-//                           the inclusive prefix; arrive READY[k&1]
-//
-// FULL is a named barrier (decode warps bar.arrive, the scan warp bar.sync),
-// READY an mbarrier the decode warps wait on: no decode warp ever waits for
-// another decode warp (with two output tiles), only for the scan warp.
-// =========================================================================
+// ---- helpers shared with K4 (hd_decode.cuh) ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t gap_nibble(const uint32_t *gap_words, uint64_t j) {
     return (__ldg(gap_words + (j >> 3)) >> (4u * (uint32_t)(j & 7))) & 15u;
 }
@@ -178,13 +121,21 @@ constexpr uint32_t kBarFull = 1, kBarReady = 3, kBarDecode = 5;
 // the nearest published PREFIX is typically one "generation" (~#SMs tiles) back:
 // a 32-wide window would need ~5 serial L2 round trips per tile, this needs one.
 // Only slots nearer than the nearest prefix are waited for.
-__device__ __forceinline__ uint64_t lookback_wide(const uint64_t *status, uint64_t tile, uint32_t lane, uint32_t *polls = nullptr) {
+// The wait is bounded (kLookbackMaxPolls rounds of ~1 us): a predecessor that never publishes -- a CTA of the
+// persistent grid that is not running, which the ticket scheme rules out, or a corrupted workspace -- raises *stuck
+// instead of hanging the GPU; the decode then finishes with wrong offsets and the entry points that synchronise
+// report HD_ERR_UNRESOLVED.
+constexpr uint32_t kLookbackMaxPolls = 1u << 22;
+__device__ __forceinline__ uint64_t lookback_wide(const uint64_t *status, uint64_t tile, uint32_t lane, uint32_t *stuck) {
     uint64_t excl = 0;
     uint32_t n_polls = 0;
     int64_t hi = (int64_t)tile - 1;
     for (;;) {
         const int64_t first = hi - 8 * (int64_t)lane;
-        ++n_polls;
+        if (++n_polls > kLookbackMaxPolls) {
+            if (lane == 0) atomicExch(stuck, 1u);
+            break;
+        }
         uint64_t v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -217,307 +168,7 @@ __device__ __forceinline__ uint64_t lookback_wide(const uint64_t *status, uint64
         if (m_found) break;
         hi -= 256;
     }
-    if (polls) *polls = n_polls;
     return excl;
-}
-
-template <int NT, int SEGS, bool LONG>
-__global__ void __launch_bounds__(NT + 32, 1) hd_decode_write_kernel(const DecodeParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    constexpr uint32_t kNW = NT / 32;
-    constexpr uint32_t kRowBytes = NT * 4;
-    constexpr uint32_t kInRows = 4 * SEGS + 3;
-    const uint32_t t = threadIdx.x;
-    const uint32_t lane = t & 31, warp = t >> 5;
-    const uint32_t lm = p.table.lut_bits;
-    const uint32_t lut_bytes = 4u << lm;
-    // where this launch's output starts (chained pieces: written by the previous launch on the stream)
-    const uint64_t out_off = p.out_offset_in ? *p.out_offset_in : 0ull;
-    uint8_t *const out = p.out + out_off;
-    const uint64_t n_symbols = p.n_symbols > out_off ? p.n_symbols - out_off : 0ull;
-
-    uint32_t *s_lut = reinterpret_cast<uint32_t *>(smem);
-    uint8_t *s_order = smem + lut_bytes;
-    LongTables *s_long = reinterpret_cast<LongTables *>(s_order + 256);
-    uint32_t off = lut_bytes + (LONG ? 256u + ((uint32_t)(sizeof(LongTables) + 15) & ~15u) : 0u);
-    uint32_t *s_in = reinterpret_cast<uint32_t *>(smem + off);
-    off += kInRows * kRowBytes;
-    // staging rows must start on a row-size boundary of the shared window (see decode_chunk)
-    const uint32_t smem_abs = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t stage_abs = (smem_abs + off + kRowBytes - 1u) & ~(kRowBytes - 1u);
-    const uint32_t stage_buf_bytes = p.stage_words * kRowBytes;
-    uint8_t *s_stage = smem + (stage_abs - smem_abs);
-    uint8_t *s_tile = s_stage + 2u * stage_buf_bytes;   // two output tiles of p.tile_bytes each
-
-    __shared__ uint32_t s_wtot[2][kNW];   // warp totals of the tile in buffer b; the scan warp turns them into exclusive offsets
-    __shared__ uint32_t s_tileid[3];   // ring: tile of step k in slot k % 3 (taken by decode thread 0 one step ahead)
-    __shared__ unsigned long long s_base[2];
-    __shared__ uint32_t s_total[2];
-    __shared__ uint32_t s_sum[2], s_arrived[2];   // tile total / number of warps that added theirs
-    // s_ready[b] completes its n-th phase once the prefix of step k = b + 2n is in s_base[b].  Parity waits are safe:
-    // the scan warp cannot finish step k+2 (the next phase of the same barrier) before every decode warp has arrived
-    // at FULL of step k+1, i.e. has long left its wait for step k.
-    __shared__ __align__(8) unsigned long long s_ready[2];
-    __shared__ uint32_t s_t1_ready;               // the tile of step 1 is in s_tileid[1]
-
-    // Tickets: every tile id comes from the atomic counter, so tiles are only ever claimed by CTAs that are running
-    // (no assumption that the whole grid is co-resident).  The FIRST ticket is taken here, before the tables are
-    // staged, the SECOND by the scan warp after that (below): by then every CTA has its first tile, so a CTA's first
-    // look-back depends only on tiles that are decoded in the same step by the other CTAs, not on second tiles.
-    if (t == NT) s_tileid[0] = atomicAdd(p.tile_counter, 1u);
-    // ---- stage the tables once per CTA (persistent) ----
-    if (t < 2) { s_sum[t] = 0; s_arrived[t] = 0; mbar_init(&s_ready[t], 1u); }
-    if (t == 0) s_t1_ready = 0;
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.table.blob);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-        for (uint32_t i = t; i < lut_bytes / 16; i += NT + 32) dst[i] = __ldg(src + i);
-        if (LONG) {
-            if (t < 64) reinterpret_cast<uint32_t *>(s_order)[t] = __ldg(reinterpret_cast<const uint32_t *>(p.table.blob + p.table.off_order) + t);
-            if (t < sizeof(LongTables) / 4) reinterpret_cast<uint32_t *>(s_long)[t] = __ldg(reinterpret_cast<const uint32_t *>(p.table.blob + p.table.off_long) + t);
-        }
-    }
-    __syncthreads();
-
-    if (t >= NT) {
-        // ======================= scan warp =======================
-        if (lane == 0) {
-            s_tileid[1] = atomicAdd(p.tile_counter, 1u);
-            __threadfence_block();
-            st_release_cta_u32(&s_t1_ready, 1u);
-        }
-        __syncwarp();
-        for (uint32_t k = 0;; ++k) {
-            const uint32_t b = k & 1u;
-            // (slot k % 3 was written by decode thread 0 during step k-1 and is not rewritten before step k+2)
-            const uint64_t tile = s_tileid[k % 3u];
-            if (tile >= p.n_tiles) break;
-            const bool tr = p.trace && blockIdx.x == kTraceCta && k < kTraceSteps && lane == 0;
-            named_bar_sync(kBarFull + b, NT + 32);
-            // ticket of step k+2 (steps 0 and 1 got theirs in the prologue).  Issued here, but no earlier: a tile must
-            // not be claimed long before it is decoded, or every higher tile's look-back waits for it.
-            uint32_t ticket = 0;
-            if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u);
-            if (tr) p.trace[k * 8 + 4] = gtime_ns();
-            const uint32_t wt = lane < kNW ? s_wtot[b][lane] : 0u;
-            uint32_t wi = wt;
-#pragma unroll
-            for (int d = 1; d < (int)kNW; d <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
-                if (lane >= (uint32_t)d) wi += v;
-            }
-            if (lane < kNW) s_wtot[b][lane] = wi - wt;   // exclusive warp offsets
-            const uint64_t agg = __shfl_sync(0xffffffffu, wi, kNW - 1);
-            // (the tile AGGREGATE was already published by the last decode warp to finish; tile 0 published its PREFIX.)
-            // Looking back BEFORE the tile is full, while the predecessors are still being decoded, was measured and is
-            // slower: 148 scan warps polling the same few L2 lines delay the very publications they wait for.
-            uint64_t excl = 0;
-            if (HD_WHATIF & 8) excl = tile * 22040ull;   // ~ the true mean of the bench workload (a larger constant would clamp tiles away)
-            if (tile > 0 && !(HD_WHATIF & 8)) {
-                uint32_t polls = 0;
-                excl = lookback_wide(p.tile_status, tile, lane, &polls);
-                if (tr) p.trace[k * 8 + 2] = polls;
-                if (lane == 0) red_max_gpu_u64(p.tile_status + tile * kStatusStride, kFlagPrefix | (excl + agg));
-            }
-            if (lane == 0) {
-                s_base[b] = excl;
-                s_total[b] = (uint32_t)agg;
-                if (tile + 1 == p.n_tiles) {
-                    uint64_t tot = excl + agg;
-                    tot = tot < n_symbols ? tot : n_symbols;
-                    if (p.count_out) *p.count_out = tot;
-                    if (p.out_offset_out) *p.out_offset_out = out_off + tot;
-                    if (p.shard_info) {
-                        p.shard_info[0] = tot;
-                        p.shard_info[1] = p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit;
-                        p.shard_info[2] = gap_nibble(p.gap_words, p.n_segments - 1);   // where the parse leaves the shard
-                    }
-                }
-            }
-            if (tr) { p.trace[k * 8 + 5] = gtime_ns(); p.trace[k * 8 + 6] = tile; }
-            // slot (k+2)%3 held step k-1's tile, which nobody reads any more
-            if (lane == 0) s_tileid[(k + 2u) % 3u] = ticket;
-            __syncwarp();
-            __threadfence_block();
-            if (lane == 0) mbar_arrive(&s_ready[b]);
-        }
-        return;
-    }
-
-    // ======================= decode warps =======================
-    DecodeTables T;
-    T.lut = s_lut;
-    T.idx_shift = 32 - lm;
-    T.lut_bits = lm;
-    T.one = lm != 0xffffffffu;   // 1 for every real table; ptxas cannot fold it
-    T.len_tab = nullptr;
-    T.lt = s_long;
-    T.order = s_order;
-    uint32_t *const col = s_in + t;
-    bool store_pending = false, prev_valid = false;
-    uint32_t prev_cnt = 0, prev_incl = 0;
-
-    // Inputs of the NEXT tile are prefetched into registers while the previous tile is compacted and flushed,
-    // so that the DRAM latency of the unit loads is off the critical path of a step.
-    uint4 pf_w[SEGS];
-    uint2 pf_la = make_uint2(0u, 0u);
-    // raw gap words + nibble shifts; the nibbles are extracted when the step starts so that the prefetch itself
-    // never waits for a load.  pf_bits == 0: this thread has no chunk in the tile.
-    uint32_t pf_gw0 = 0, pf_gw1 = 0, pf_sh = 0, pf_bits = 0;
-    auto prefetch = [&](uint64_t tile) {
-        pf_bits = 0;
-        if (tile >= p.n_tiles) return;
-        const uint64_t g0 = (tile * NT + t) * SEGS;
-        if (g0 >= p.n_segments) return;
-        const uint64_t left = p.n_segments - g0;
-        const uint32_t nseg = left < (uint64_t)SEGS ? (uint32_t)left : (uint32_t)SEGS;
-        const uint64_t u0 = g0 * 4;
-#pragma unroll
-        for (int q = 0; q < SEGS; ++q) {
-            const uint64_t u = u0 + 4u * q;
-            uint4 w = make_uint4(0u, 0u, 0u, 0u);
-            if (u + 4 <= p.n_units) {
-                w = __ldg(reinterpret_cast<const uint4 *>(p.units + u));
-            } else if (u < p.n_units) {
-                w.x = __ldg(p.units + u);
-                if (u + 1 < p.n_units) w.y = __ldg(p.units + u + 1);
-                if (u + 2 < p.n_units) w.z = __ldg(p.units + u + 2);
-            }
-            pf_w[q] = w;
-        }
-        {   // look-ahead: the first two units of the next chunk
-            const uint64_t u = u0 + 4u * SEGS;
-            uint2 w = make_uint2(0u, 0u);
-            if (u + 2 <= p.n_units) w = __ldg(reinterpret_cast<const uint2 *>(p.units + u));
-            else if (u < p.n_units) w.x = __ldg(p.units + u);
-            pf_la = w;
-        }
-        const uint64_t j1 = g0 + nseg - 1;   // gap element = entry offset of the NEXT chunk
-        pf_gw1 = __ldg(p.gap_words + (j1 >> 3));
-        uint32_t sh0 = 0;
-        if (g0 == 0) {
-            pf_gw0 = p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit;
-        } else {
-            pf_gw0 = __ldg(p.gap_words + ((g0 - 1) >> 3));
-            sh0 = 4u * (uint32_t)((g0 - 1) & 7);
-        }
-        pf_sh = sh0 | (4u * (uint32_t)(j1 & 7)) << 8;
-        pf_bits = nseg * kSegmentBits;
-    };
-    prefetch(s_tileid[0]);
-
-    for (uint32_t k = 0;; ++k) {
-        const uint32_t b = k & 1u;
-        const uint64_t tile = s_tileid[k % 3u];
-        const bool valid = tile < p.n_tiles;
-        uint32_t cnt = 0, incl = 0;
-        const bool tr = p.trace && blockIdx.x == kTraceCta && k < kTraceSteps && t == 0;
-        if (tr) p.trace[k * 8 + 0] = gtime_ns();
-        if (valid) {
-            // ---------------- decode this thread's chunk (units were prefetched) ----------------
-            if (pf_bits) {
-                const uint32_t pf_entry = (pf_gw0 >> (pf_sh & 31u)) & 15u;
-                const uint32_t pf_stop = pf_bits + ((pf_gw1 >> (pf_sh >> 8)) & 15u);
-#pragma unroll
-                for (int q = 0; q < SEGS; ++q) {
-                    col[(4 * q + 0) * NT] = pf_w[q].x;
-                    col[(4 * q + 1) * NT] = pf_w[q].y;
-                    col[(4 * q + 2) * NT] = pf_w[q].z;
-                    col[(4 * q + 3) * NT] = pf_w[q].w;
-                }
-                col[(4 * SEGS + 0) * NT] = pf_la.x;
-                col[(4 * SEGS + 1) * NT] = pf_la.y;
-                if (tr) p.trace[k * 8 + 7] = gtime_ns();
-                cnt = (HD_WHATIF & 4) ? 43u : decode_chunk<NT, LONG>(col, pf_entry, pf_stop, T, stage_abs + b * stage_buf_bytes + t * 4u, nullptr);
-            }
-            // ---------------- warp-wide inclusive scan of the counts ----------------
-            incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= (uint32_t)d) incl += v;
-            }
-            // this warp's TMA store of two steps ago read the tile buffer that is written again next step
-            if (store_pending) { tma_bulk_wait_read0(); store_pending = false; }
-            if (lane == 31) {
-                s_wtot[b][warp] = incl;
-                // the last warp to finish publishes the tile aggregate right away (tile 0: it is its own prefix)
-                atomicAdd(&s_sum[b], incl);
-                __threadfence_block();
-                if (atomicAdd(&s_arrived[b], 1u) == kNW - 1) {
-                    const uint32_t total = atomicExch(&s_sum[b], 0u);
-                    s_arrived[b] = 0;
-                    red_max_gpu_u64(p.tile_status + tile * kStatusStride, (tile == 0 ? kFlagPrefix : kFlagAggregate) | (uint64_t)total);
-                }
-            }
-            __threadfence_block();
-            if (tr) p.trace[k * 8 + 1] = gtime_ns();
-            named_bar_arrive(kBarFull + b, NT + 32);
-        }
-        if (prev_valid) {
-            if (p.tile_buffers == 1u) {
-                // single output tile: every warp's TMA store of the previous step must have finished reading it
-                // before any warp compacts into it again
-                if (store_pending) { tma_bulk_wait_read0(); store_pending = false; }
-                named_bar_sync(kBarDecode, NT);
-            }
-            // wait for the scan warp's prefix of tile k-1 (computed while we decoded tile k): a flag, not a
-            // barrier, so that with two output tiles no decode warp ever waits for another decode warp
-            mbar_wait(&s_ready[b ^ 1u], ((k - 1u) >> 1) & 1u);
-        }
-        if (k == 0) {
-            while (ld_acquire_cta_u32(&s_t1_ready) == 0) __nanosleep(100);   // the scan warp's second ticket
-        }
-        if (valid) prefetch(s_tileid[(k + 1u) % 3u]);   // published with s_t1_ready / s_ready above
-        if (prev_valid && !(HD_WHATIF & 1)) {
-            // ---------------- finish tile k-1: compact this WARP's symbols and flush them ----------------
-            const uint32_t pb = b ^ 1u;
-            const uint64_t base = s_base[pb];
-            const uint32_t woff = s_wtot[pb][warp];                            // this warp's offset in the tile
-            const uint32_t wtot = __shfl_sync(0xffffffffu, prev_incl, 31);     // this warp's symbols
-            const uint32_t excl_t = woff + prev_incl - prev_cnt;
-            // clamp to n_symbols (pad bits decode to garbage: reference clamps with
-            // out_pos < next_out_pos, cuhd_gpu_decoder.cu:101-105)
-            const uint64_t my_off = base + excl_t;
-            uint32_t c = prev_cnt;
-            if (my_off >= n_symbols) c = 0;
-            else if (my_off + c > n_symbols) c = (uint32_t)(n_symbols - my_off);
-            const uint32_t A = (uint32_t)((reinterpret_cast<uintptr_t>(out) + base) & 15u);
-            uint8_t *tile_buf = s_tile + (p.tile_buffers == 2u ? pb * p.tile_bytes : 0u);
-            if (c && !(HD_WHATIF & 16)) compact_to_tile(reinterpret_cast<const uint32_t *>(s_stage + pb * stage_buf_bytes) + t, NT, c, tile_buf, A + excl_t);
-            if (!(HD_WHATIF & 128)) fence_proxy_async_smem();
-            __syncwarp();
-            // flush: the warp's span is contiguous in the tile and in the output, and both have the same 16-byte
-            // phase -> one TMA bulk store for the aligned body, lanes 0-15 / 16-31 for head / tail bytes
-            const uint64_t wbase = base + woff;
-            uint64_t lim = wbase >= n_symbols ? 0 : n_symbols - wbase;
-            const uint32_t total = wtot < lim ? wtot : (uint32_t)lim;
-            const uint8_t *sp = tile_buf + A + woff;
-            uint8_t *gp = out + wbase;
-            uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(gp) & 15u)) & 15u;
-            if (head > total) head = total;
-            const uint32_t body = (total - head) & ~15u;
-            const uint32_t tail = total - head - body;
-            if (lane == 0 && body && !(HD_WHATIF & 32)) {
-                tma_bulk_store(gp + head, sp + head, body);
-                tma_bulk_commit();
-                store_pending = true;
-            }
-            if (HD_WHATIF & 64) {
-            } else if (lane < 16) {
-                if (lane < head) gp[lane] = sp[lane];
-            } else {
-                const uint32_t i = lane - 16;
-                if (i < tail) gp[head + body + i] = sp[head + body + i];
-            }
-        }
-        if (tr) p.trace[k * 8 + 3] = gtime_ns();
-        if (!valid) break;
-        prev_valid = true;
-        prev_cnt = cnt;
-        prev_incl = incl;
-    }
-    if (store_pending) tma_bulk_wait0();
 }
 
 // =========================================================================
@@ -605,13 +256,12 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// loads the four units of (global) segment s from a warp's staged, padded tile that starts at segment q0
+// loads the four units of (global) segment s from a warp's staged tile (layout: hd_internal.h) that starts at segment q0
 struct TileSegLoader {
     const uint4 *tile;
     int64_t q0;
     __device__ __forceinline__ Seg4 operator()(uint64_t s) const {
-        const uint32_t i = (uint32_t)((int64_t)s - q0);
-        const uint4 w = tile[i + (i >> 4)];
+        const uint4 w = tile[sync_phys_unit((uint32_t)((int64_t)s - q0))];
         Seg4 r;
         r.x = w.x; r.y = w.y; r.z = w.z; r.w = w.w;
         return r;
@@ -626,6 +276,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 *tile = reinterpret_cast<uint4 *>(smem + sync_tables_bytes(p.table.lut_bits) + (size_t)warp * kSyncTileBytes);
+    const uint32_t land_abs = (uint32_t)__cvta_generic_to_shared(tile + kSyncTilePhysUnits);   // landing bytes [slot][lane]
     const uint64_t n_units16 = (p.n_units + 3) >> 2;   // 16-byte units that hold stream data (last one may be partial)
 
     // ---- the seam between two warp tiles.  Lane 1 of tile t entered its chunk with the exit lane 0 computed for the
@@ -681,51 +332,51 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
         const uint64_t chunk0 = (uint64_t)ticket * kSyncTileChunks;   // lane 0's chunk (owned by the previous tile)
         const int64_t q0 = (int64_t)(chunk0 * kSyncChunkSegs) - kSyncHaloSegs;
         __syncwarp();   // every lane is done reading the previous tile
-        for (uint32_t i = lane; i < kSyncTileUnits16; i += 32) {
+        const bool interior = q0 >= 0 && (uint64_t)q0 + kSyncTileSrcUnits <= (p.n_units >> 2);   // every unit is whole
+#pragma unroll 1
+        for (uint32_t i = lane; i < kSyncTileSrcUnits; i += 32) {
             const int64_t q = q0 + i;
-            uint32_t bytes = 0;
-            if (q >= 0 && (uint64_t)q < n_units16) {
-                const uint64_t rem = p.n_units - (uint64_t)q * 4;
-                bytes = rem >= 4 ? 16u : (uint32_t)rem * 4u;
+            uint32_t bytes = 16;
+            if (!interior) {
+                bytes = 0;
+                if (q >= 0 && (uint64_t)q < n_units16) {
+                    const uint64_t rem = p.n_units - (uint64_t)q * 4;
+                    bytes = rem >= 4 ? 16u : (uint32_t)rem * 4u;
+                }
             }
             // (a source address is needed even when nothing is copied)
-            cp_async16_zfill(tile + i + (i >> 4), p.units + (bytes ? (uint64_t)q * 4 : 0), bytes);
+            const uint32_t *src = p.units + (bytes ? (uint64_t)q * 4 : 0);
+            uint4 *dst = tile + sync_phys_unit(i);
+            cp_async16_zfill(dst, src, bytes);
+            // the first unit of a chunk also goes into the slot behind the previous region (or the tile halo)
+            if (i >= kSyncHaloSegs && ((i - kSyncHaloSegs) & (kSyncChunkSegs - 1)) == 0) cp_async16_zfill(dst - 1, src, bytes);
         }
         cp_async_commit_wait_all();
         __syncwarp();
 
-        // ---- parse: 4 halo segments from bit 0, then the 16 segments of the chunk ----
+        // ---- parse: 4 halo segments from bit 0, then the 16 segments of the chunk: two flattened runs ----
         const uint64_t chunk = chunk0 + lane;
         const bool active = chunk < p.n_chunks;
         const bool owner = active && (lane > 0 || ticket == 0);
         uint32_t words[2] = {0u, 0u};
         uint32_t entry = 0;
         if (active && !(HD_WHATIF & 256)) {
-            uint32_t i = kSyncChunkSegs * lane;   // unit index (within the staged tile) of the halo start
-            uint32_t pos = 0;
-            if (chunk == 0) {
-                pos = p.first_bit;                // the stream's first chunk starts at a known offset: no halo
-                i += kSyncHaloSegs;
-            } else {
-#pragma unroll 1
-                for (uint32_t h = 0; h < kSyncHaloSegs; ++h, ++i) {
-                    const uint4 w = tile[i + (i >> 4)];
-                    const uint32_t n = tile[i + 1 + ((i + 1) >> 4)].x;
-                    pos = sync_segment<EXACT, LONG>(w.x, w.y, w.z, w.w, n, pos, L);
-                }
+            const uint32_t *region = reinterpret_cast<const uint32_t *>(tile + kSyncHaloSegs + 1 + kSyncRegionUnits * lane);
+            uint32_t pos = p.first_bit;   // the stream's first chunk starts at a known offset: no halo
+            if (chunk != 0) {
+                // the halo = the 4 units before the region (lane 0: the tile halo), followed by a copy of the chunk's
+                // first unit
+                pos = sync_run<EXACT, LONG, false>(region - 4 * (kSyncHaloSegs + 1), 0u, kSyncHaloSegs * kSegmentBits, L, 0u, nullptr) -
+                      kSyncHaloSegs * kSegmentBits;
             }
             entry = pos;
-#pragma unroll 1
-            for (uint32_t g = 0; g < kSyncChunkSegs / 8; ++g) {
-                uint32_t word = 0;
+            sync_run<EXACT, LONG, true>(region, entry, kSyncChunkSegs * kSegmentBits, L, land_abs + 32u + lane, nullptr);
+            // landings into segments 1..16 of the chunk (slot k = landing into segment k)
 #pragma unroll
-                for (uint32_t k = 0; k < 8; ++k, ++i) {
-                    const uint4 w = tile[i + (i >> 4)];
-                    const uint32_t n = tile[i + 1 + ((i + 1) >> 4)].x;
-                    pos = sync_segment<EXACT, LONG>(w.x, w.y, w.z, w.w, n, pos, L);
-                    word |= pos << (4u * k);
-                }
-                words[g] = word;
+            for (uint32_t k = 0; k < kSyncChunkSegs; ++k) {
+                uint32_t b;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(land_abs + 32u * (k + 1u) + lane));
+                words[k >> 3] |= (b & 15u) << (4u * (k & 7u));
             }
         }
         // ---- seams inside the warp tile: a lane whose halo parse had not merged yet (~20 % at the reference's

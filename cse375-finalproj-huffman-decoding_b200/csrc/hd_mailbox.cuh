@@ -4,6 +4,12 @@
 // every peer's mailbox (one tiny kernel, st.release.sys); a rank has the all-gather as soon as every slot of its own
 // mailbox carries the current sequence number (one tiny kernel, ld.acquire.sys).  ~3 us instead of ~40 us for an
 // 8-rank ncclAllGather of 24 bytes, and no host involvement.  (the exchange is 8-16 B per GPU.)
+//
+// Every rank has TWO slots per peer, used alternately (round `seq` goes to slot seq & 1).  A rank can publish round
+// n+2 only after its own wait of round n+1 returned (stream order), which needs every peer's publication of round
+// n+1, which those peers enqueue behind their wait of round n: so a slot is overwritten only after all its readers
+// are done with it, without any acknowledgement traffic.  The reader still re-checks the sequence number after
+// copying the slot and reports a protocol violation (a caller that published out of order) instead of torn data.
 #ifndef HD_MAILBOX_CUH_
 #define HD_MAILBOX_CUH_
 
@@ -14,6 +20,7 @@ namespace hd {
 
 constexpr uint32_t kMailboxSlotWords = 4;      // {count, entry, exit, seq}
 constexpr uint32_t kMailboxMaxWorld = 64;
+constexpr uint32_t kMailboxRing = 2;           // slots per peer, indexed by seq % kMailboxRing
 
 struct MailboxPeers {
     unsigned long long *buf[kMailboxMaxWorld];   // buf[p] = base of rank p's mailbox (peer-mapped; own entry = local)
@@ -33,7 +40,7 @@ __global__ void hd_mailbox_publish_kernel(MailboxPeers peers, uint32_t world, ui
                                           unsigned long long seq) {
     const uint32_t p = threadIdx.x;
     if (p >= world) return;
-    unsigned long long *slot = peers.buf[p] + (size_t)rank * kMailboxSlotWords;
+    unsigned long long *slot = peers.buf[p] + ((size_t)rank * kMailboxRing + (seq % kMailboxRing)) * kMailboxSlotWords;
     slot[0] = info3[0];
     slot[1] = info3[1];
     slot[2] = info3[2];
@@ -46,7 +53,7 @@ __global__ void hd_mailbox_wait_kernel(const unsigned long long *local, uint32_t
                                        unsigned long long *all_info3, uint32_t *timeout) {
     const uint32_t p = threadIdx.x;
     if (p >= world) return;
-    const unsigned long long *slot = local + (size_t)p * kMailboxSlotWords;
+    const unsigned long long *slot = local + ((size_t)p * kMailboxRing + (seq % kMailboxRing)) * kMailboxSlotWords;
     unsigned long long spins = 0;
     while (ld_acquire_sys_u64(slot + 3) < seq) {
         __nanosleep(200);
@@ -55,9 +62,14 @@ __global__ void hd_mailbox_wait_kernel(const unsigned long long *local, uint32_t
             return;
         }
     }
-    all_info3[p * 3 + 0] = slot[0];
-    all_info3[p * 3 + 1] = slot[1];
-    all_info3[p * 3 + 2] = slot[2];
+    const unsigned long long a = slot[0], b = slot[1], c = slot[2];
+    if (ld_acquire_sys_u64(slot + 3) != seq) {   // overwritten while it was read: rounds were published out of order
+        if (timeout) *timeout = 2;
+        return;
+    }
+    all_info3[p * 3 + 0] = a;
+    all_info3[p * 3 + 1] = b;
+    all_info3[p * 3 + 2] = c;
 }
 
 }  // namespace hd

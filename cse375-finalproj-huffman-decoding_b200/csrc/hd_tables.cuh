@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(1024) hd_build_tables_kernel(const hd_sym_len 
             bits += len1;
             count = 2;
         }
-        dec[w] = syms | (bits << 16) | (count << 24);
+        dec[w] = syms | (bits << 16) | (count << 27);   // top byte = 8 * count
         uint32_t jump = len0, l, s;
         while (jump < lm && table_first_code(w, jump, lm, lt, s_order, max_len, l, s)) jump += l;
         syn[w] = (uint16_t)(jump | (len0 << 8));

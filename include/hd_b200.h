@@ -91,8 +91,10 @@ uint32_t hd_table_min_length(const hd_table *t);
 /* --------------------------------------------------------------- workspace
  * Replaces cuhd::CUHDGPUDecoderMemory (gpuhd/src/cuhd_gpu_decoder_memory.cc:
  * 25-48: 16 B sync point + 4 B count per subsequence + flags) and the
- * per-segment output_pos array of decoder.cu:754.  Ours: 8 B per tile of 256
- * segments + (self-sync) 4 bits per 128-bit subsequence. */
+ * per-segment output_pos array of decoder.cu:754.  Ours: one 64-bit status word,
+ * padded to a 32-byte sector, per 256 segments (an upper bound: the kernel's
+ * tiles hold 512-1728 segments) + (self-sync) 4 bits per 128-bit subsequence,
+ * one byte per 16 subsequences and one word per 496. */
 size_t hd_workspace_bytes_gap(uint64_t n_units);
 size_t hd_workspace_bytes_selfsync(uint64_t n_units);
 
@@ -101,8 +103,10 @@ size_t hd_workspace_bytes_selfsync(uint64_t n_units);
  * (Huffman_coding_Gap_arrays/decoder/src/decoder.cu:454-730, 732-815;
  * declared decoder/include/decoder.cuh:4-15).  d_gap_words: ceil(n_segments/8)
  * words, element i in word i/8 bits [4(i%8),4(i%8)+3]; segment k>0 starts at
- * bit 128k+gap[k-1] (decoder.cu:505-507).  Writes exactly n_symbols bytes
- * (fewer only if the stream holds fewer codewords).  Asynchronous on stream. */
+ * bit 128k+gap[k-1] (decoder.cu:505-507).  Element n_segments-1 is read too
+ * (the offset at which the parse leaves the stream); d_gap_words may be NULL
+ * only when n_segments == 1.  Writes exactly n_symbols bytes (fewer only if the
+ * stream holds fewer codewords).  Asynchronous on stream. */
 hd_status hd_decode_gap(const uint32_t *d_units, uint64_t n_units,
                         const uint32_t *d_gap_words, uint64_t n_segments,
                         const hd_table *table, uint8_t *d_out,

@@ -65,83 +65,6 @@ struct HostSegLoader {
 
 }  // namespace
 
-// Re-enactment of hd_decode_write_kernel<NT, SEGS>: tiles of NT chunks of `segs`
-// segments; per thread: transposed input column, decode_chunk -> staging column
-// (same address arithmetic as on the device, over a host arena whose staging
-// region starts on a row boundary), exclusive scan, clamp, compact_to_tile into
-// a tile placed at the same 16-byte phase, copy out.
-template <int NT>
-static int64_t emul_decode_gap_nt(HostTables &h, const uint32_t *units, uint64_t n_units, const uint32_t *gap_words,
-                                  uint64_t n_segments, uint32_t first_bit, uint8_t *out, uint64_t n_symbols,
-                                  uint64_t out_addr_phase, uint32_t segs) {
-    const uint32_t min_len = h.blob.min_len ? h.blob.min_len : 1;
-    const uint32_t max_cnt = (kSegmentBits * segs + 15 + min_len - 1) / min_len;
-    const uint32_t stage_words = max_cnt / 4 + 3;
-    const uint32_t tile_sym = (NT * kSegmentBits * segs + 15 + min_len - 1) / min_len + 2;
-    const uint32_t tile_bytes = ((tile_sym + 32) + 15) & ~15u;
-    const uint32_t in_rows = 4 * segs + 3;
-    const uint32_t row = NT * 4;
-    std::vector<uint32_t> in((size_t)in_rows * NT);
-    std::vector<uint8_t> arena((size_t)stage_words * row + 2 * row);
-    const uint32_t stage_off = row;   // row-aligned offset inside the arena (device: aligned shared address)
-    std::vector<uint8_t> tile(tile_bytes);
-    auto nib = [&](uint64_t j) { return (gap_words[j >> 3] >> (4u * (uint32_t)(j & 7))) & 15u; };
-    const uint64_t n_chunks = (n_segments + segs - 1) / segs;
-    const uint64_t n_tiles = (n_chunks + NT - 1) / NT;
-    std::vector<uint32_t> cnt(NT);
-    uint64_t base = 0;
-    for (uint64_t tl = 0; tl < n_tiles; ++tl) {
-        // poison so that reads of never-written staging/tile bytes show up
-        std::fill(arena.begin(), arena.end(), (uint8_t)0xDE);
-        std::fill(tile.begin(), tile.end(), (uint8_t)0xEE);
-        std::fill(in.begin(), in.end(), 0xBADC0DEu);
-        for (uint32_t t = 0; t < NT; ++t) {
-            const uint64_t g0 = (tl * NT + t) * segs;
-            cnt[t] = 0;
-            if (g0 >= n_segments) continue;
-            const uint64_t left = n_segments - g0;
-            const uint32_t nseg = left < segs ? (uint32_t)left : segs;
-            uint32_t *col = in.data() + t;
-            for (uint32_t w = 0; w < 4 * segs + 2; ++w) {
-                const uint64_t u = g0 * 4 + w;
-                col[(size_t)w * NT] = u < n_units ? units[u] : 0u;
-            }
-            const uint32_t entry = g0 == 0 ? first_bit : nib(g0 - 1);
-            const uint32_t stop = nseg * kSegmentBits + nib(g0 + nseg - 1);
-            const uint32_t sa = stage_off + t * 4u;
-            uint32_t c = h.blob.has_long ? decode_chunk<NT, true>(col, entry, stop, h.T, sa, arena.data())
-                                         : decode_chunk<NT, false>(col, entry, stop, h.T, sa, arena.data());
-            if (c > max_cnt) return -2;   // staging/tile sizing assumption violated
-            if (c / 4 + 1 >= stage_words) return -5;   // compact_to_tile would read past the staging rows
-            cnt[t] = c;
-        }
-        // canary: the row after the staging rows must be untouched (a byte store past the last row lands there)
-        for (uint32_t i = 0; i < row; ++i)
-            if (arena[(size_t)stage_off + (size_t)stage_words * row + i] != 0xDE) return -6;
-        const uint32_t *stage = reinterpret_cast<const uint32_t *>(arena.data() + stage_off);
-        uint32_t excl = 0;
-        const uint32_t A = (uint32_t)((out_addr_phase + base) & 15u);
-        uint64_t tile_total = 0;
-        for (uint32_t t = 0; t < NT; ++t) {
-            uint64_t my_off = base + excl;
-            uint32_t c = cnt[t];
-            if (my_off >= n_symbols) c = 0;
-            else if (my_off + c > n_symbols) c = (uint32_t)(n_symbols - my_off);
-            if (c) {
-                if (A + excl + c > tile_bytes) return -3;
-                compact_to_tile(stage + t, NT, c, tile.data(), A + excl);
-            }
-            excl += cnt[t];
-            tile_total += cnt[t];
-        }
-        uint64_t lim = base >= n_symbols ? 0 : n_symbols - base;
-        uint64_t tot = tile_total < lim ? tile_total : lim;
-        std::memcpy(out + base, tile.data() + A, tot);
-        base += tile_total;
-    }
-    return (int64_t)(base < n_symbols ? base : n_symbols);
-}
-
 // Re-enactment of hd_decode_tiles_kernel<SEGS, RCAP> (hd_decode.cuh): warp tiles of 32 chunks; per lane: transposed
 // input column, decode_chunk<32> into the warp's staging block, then the IN-PLACE compaction exactly as the kernel
 // orders it (all lanes column_read -> all lanes column_write -> all lanes column_write_head) at the 16-byte phase of
@@ -222,14 +145,12 @@ int64_t emul_decode_gap(const uint32_t *units, uint64_t n_units, const uint32_t 
     HostTables h;
     if (!make_tables(flat, flat_bits, pairs, n_pairs, h)) return -1;
     if (segs != 1 && segs != 2 && segs != 4) return -4;
-    if (nt == 256) return emul_decode_gap_nt<256>(h, units, n_units, gap_words, n_segments, first_bit, out, n_symbols, out_addr_phase, segs);
     if (nt == 32) {
         int64_t r = emul_decode_tiles<12>(h, units, n_units, gap_words, n_segments, first_bit, out, n_symbols, out_addr_phase, segs);
         if (r == -4) r = emul_decode_tiles<24>(h, units, n_units, gap_words, n_segments, first_bit, out, n_symbols, out_addr_phase, segs);
         if (r == -4 && segs == 1) r = emul_decode_tiles<36>(h, units, n_units, gap_words, n_segments, first_bit, out, n_symbols, out_addr_phase, segs);
         return r == -4 ? -40 : r;   // -40: geometry not instantiated for this code (mirrors tile_geom in hd_api.cu)
     }
-    if (nt == 512) return emul_decode_gap_nt<512>(h, units, n_units, gap_words, n_segments, first_bit, out, n_symbols, out_addr_phase, segs);
     return -4;
 }
 
