@@ -39,6 +39,9 @@ constexpr uint32_t kSyncTilePhysUnits = kSyncHaloSegs + 1 + 32 * kSyncRegionUnit
 constexpr uint32_t kSyncLandBytes = (kSyncChunkSegs + 1) * 32;
 constexpr uint32_t kSyncTileBytes = kSyncTilePhysUnits * 16 + kSyncLandBytes;
 // physical unit of tile-relative source unit i (i = 0: first halo unit)
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
 constexpr uint32_t sync_phys_unit(uint32_t i) {
     return i < kSyncHaloSegs ? i
                              : kSyncHaloSegs + 1 + kSyncRegionUnits * ((i - kSyncHaloSegs) / kSyncChunkSegs) +
