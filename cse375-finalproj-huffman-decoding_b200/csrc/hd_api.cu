@@ -255,6 +255,10 @@ hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32
     q.count_out = d_count;
     q.stage_rows = g.stage_rows;
     q.n_warps = g.n_warps;
+    q.k_one = 1u;
+    q.k_sel_len = kSelLen;
+    q.k_sel_cnt8 = kSelCnt8;
+    q.k_pair_slope = kPairSelSlope;
     if (!already_zeroed) HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes, s));
     ProfScope prof(HD_PROFILE_DECODE_WRITE, s);
     return table->host.has_long ? launch_tiles_geom<true>(g, q, s) : launch_tiles_geom<false>(g, q, s);
@@ -422,7 +426,7 @@ hd_status hd_table_from_lengths(const hd_sym_len *pairs, uint32_t n_pairs, void 
     return upload_table(c, stream, out);
 }
 
-// K0: the whole blob is built by a kernel from a DEVICE-resident {symbol,length} list; only a 16-byte summary comes
+// K0: the whole blob is built by a kernel from a DEVICE-resident {symbol,length} list; only a 20-byte summary comes
 // back (the host needs lut_bits / min_len / max_len to pick kernel variants and shared-memory geometry).
 hd_status hd_table_from_lengths_device(const hd_sym_len *d_pairs, uint32_t n_pairs, void *stream, hd_table **out) {
     if (!out || !d_pairs || n_pairs == 0 || n_pairs > 256) return HD_ERR_INVALID;
@@ -430,7 +434,7 @@ hd_status hd_table_from_lengths_device(const hd_sym_len *d_pairs, uint32_t n_pai
     hd_table *t = new (std::nothrow) hd_table();
     if (!t) return HD_ERR_INVALID;
     TableSummary *d_sum = nullptr;
-    TableSummary h_sum = {0, 0, 0, 0};
+    TableSummary h_sum = {0, 0, 0, 0, 0};
     cudaError_t e = cudaGetDevice(&t->device);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&t->d_blob), kTableBlobMaxBytes);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&d_sum), sizeof(TableSummary));
@@ -454,7 +458,7 @@ hd_status hd_table_from_lengths_device(const hd_sym_len *d_pairs, uint32_t n_pai
     b.lut_bits = h_sum.lut_bits;
     b.min_len = h_sum.min_len;
     b.max_len = h_sum.max_len;
-    b.has_long = h_sum.max_len > h_sum.lut_bits ? 1u : 0u;
+    b.has_long = h_sum.has_long;
     b.off_sync = n * 4;
     b.off_len = b.off_sync + n * 2;
     b.off_order = b.off_len + 256;

@@ -34,15 +34,15 @@ HD_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {
 
 // Canonical resolver for codes longer than the primary LUT (len in
 // (lut_bits, 16]).  win = next 32 stream bits, left aligned.  Returns a
-// synthesized primary entry {sym, 0, bits=len, 8 * count = 8}, or a 1-bit skip for a
+// synthesized primary entry (one symbol), or a 1-bit skip without symbols for a
 // window that matches no code (hole of an incomplete code).
 HD_HD uint32_t resolve_long(uint32_t win, uint32_t lut_bits, const LongTables *lt, const uint8_t *order) {
     for (uint32_t len = lut_bits + 1; len <= kMaxCodeLen; ++len) {
         const uint32_t c = win >> (32 - len);
         const uint32_t d = c - lt->first[len];
-        if (d < lt->count[len]) return (uint32_t)order[lt->offset[len] + d] | (len << 16) | (8u << 24);
+        if (d < lt->count[len]) return lut_entry(len, order[lt->offset[len] + d], 0u, 1u);
     }
-    return 1u << 16;
+    return lut_entry(1u, 0u, 0u, 0u);
 }
 
 struct DecodeTables {
@@ -50,6 +50,7 @@ struct DecodeTables {
     uint32_t idx_shift;      // 32 - lut_bits
     uint32_t lut_bits;
     uint32_t one;            // the constant 1, opaque to the compiler (see decode_chunk)
+    uint32_t sel_len, sel_cnt8, pair_slope;   // kSelLen, kSelCnt8, kPairSelSlope in registers (not re-materialised per iteration)
     const uint8_t *len_tab;  // code length by symbol
     const LongTables *lt;
     const uint8_t *order;
@@ -88,13 +89,29 @@ inline uint32_t smem_ld_u32(uint32_t a, const uint8_t *arena) { uint32_t v; memc
 HD_CONSTEXPR uint32_t col_bits(uint32_t nt) { return (nt - 1u) << 2; }
 HD_CONSTEXPR uint32_t row_shift(uint32_t nt) { return nt == 512 ? 11u : nt == 256 ? 10u : nt == 128 ? 9u : nt == 32 ? 7u : 0u; }
 
-HD_HD uint32_t byte2(uint32_t e) {
+// c + byte k of e (k given as the dp4a selector 1 << 8k): ONE instruction on the FMA pipe (IDP.4A)
+HD_HD uint32_t add_byte(uint32_t e, uint32_t sel, uint32_t c) {
 #if defined(__CUDA_ARCH__)
-    return __byte_perm(e, 0u, 0x4442u);   // one PRMT instead of shift + mask
+    return __dp4a(e, sel, c);
 #else
-    return (e >> 16) & 0xffu;
+    uint32_t r = c;
+    for (int k = 0; k < 4; ++k) r += ((e >> (8 * k)) & 0xffu) * ((sel >> (8 * k)) & 0xffu);
+    return r;
 #endif
 }
+HD_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;   // (PTX directly: __byte_perm masks the selector first, one more ALU instruction)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) r |= (uint32_t)((v >> (8 * ((sel >> (4 * k)) & 7u))) & 0xffu) << (8 * k);
+    return r;
+#endif
+}
+constexpr uint32_t kSelLen = 0x00000001u, kSelCnt8 = 0x01000000u;   // dp4a selectors of the entry's length / 8 * count bytes
 
 // a + k as a multiply-add with an OPAQUE multiplier register holding 1: it issues on the FMA pipe.  The decode loop is
 // bound by the INT (ALU) pipe, which retires one warp instruction every two cycles; written as an add the compiler
@@ -111,7 +128,7 @@ __device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t one, uint32_t k
 // Decode one chunk (SEGS consecutive 128-bit segments of one thread) in a single
 // flattened loop.  The chunk's units sit in the thread's column of the
 // transposed input block: word w at in_col[w * NT] (conflict-free refills);
-// words past the chunk (the next chunk's first two) must be present.
+// the two words past the chunk (the next chunk's first two) must be present.
 // Decoding starts at bit `entry` (< 32) and runs until the position reaches
 // `stop` = chunk bits + entry offset of the NEXT chunk, i.e. exactly to the
 // codeword boundary at which the successor starts (with an exact gap array this
@@ -119,15 +136,25 @@ __device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t one, uint32_t k
 // the chunk -- because the last such codeword ends at that boundary).
 //
 // Two table steps per window slide: a step consumes at most 16 bits, so the 32-bit
-// window taken at `pos` still holds the 16 bits the second step looks at
-// (win << bits1); the second step is dropped when the first reached `stop`.  The
-// <= 4 symbols of the two steps are packed behind the bytes still pending in a
-// register (P, np8 = 8 * pending bytes) and a full 32-bit word is stored to the
+// window taken at `pos` still holds the 16 bits the second step looks at.  BOTH
+// steps always run -- the loop has no "did the first step reach stop?" test; what a
+// pair decodes past `stop` (at most the second symbol of the step that reaches it
+// and the whole step after it) is taken off the count after the loop and its bytes
+// land in staging slack.  The <= 4 symbols of a pair are merged with one byte
+// permute, shifted behind the bytes still pending in a register (P; n8 = 8 * symbols
+// so far, used modulo 32 by wrapping shifts) and a full 32-bit word is stored to the
 // thread's staging column (word m at stage_addr + m * NT * 4: bank == lane, conflict
-// free) whenever four symbols are complete: ONE shared-memory store per four
-// symbols instead of one per symbol -- the kernel is bound by shared-memory
-// wavefronts.  LUT entries are {sym0, sym1, bits, 8 * count}.
-// Returns the number of symbols; staging words [0, ceil(count / 4)] are written.
+// free) whenever four symbols are complete.  The loop is bound by the ALU pipe
+// (shifts, logic, permutes: one warp instruction per 2 cycles); everything that can
+// be an add goes to the FMA pipe instead (dp4a byte adds, multiply-adds, predicated
+// moves).  Returns the number of symbols; staging words [0, ceil((count + 3) / 4)]
+// may be written.
+constexpr uint32_t kPairSel2 = 0x6521u;   // first step has two symbols: {e1.s0, e1.s1, e2.s0, e2.s1}
+constexpr uint32_t kPairSel1 = 0x2651u;   // one symbol: {e1.s0, e2.s0, e2.s1, e1.s1 (= 0)}
+constexpr uint32_t kPairSelSlope = (kPairSel2 - kPairSel1) / 8u;   // selector = base + slope * (8 * count): 8 -> Sel1, 16 -> Sel2
+constexpr uint32_t kPairSelBase = kPairSel1 - 8u * kPairSelSlope;
+static_assert(kPairSelBase + 16u * kPairSelSlope == kPairSel2, "pair selector is linear in the count byte");
+
 template <int NT, bool LONG>
 HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t stop, const DecodeTables &T,
                             uint32_t stage_addr, uint8_t *arena) {
@@ -140,46 +167,64 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
     const uint32_t *nxt = in_col + 2 * NT;
 #endif
     uint32_t R = stage_addr;   // where the next full word goes
-    uint32_t P = 0, np8 = 0;   // pending symbols (low np8 / 8 bytes of P), np8 < 32
+    uint32_t P = 0, n8 = 0;    // pending symbols (low (n8 & 31) / 8 bytes of P); n8 = 8 * symbols so far
     uint32_t pos = entry;
-    uint32_t e = 0;
-    while (pos < stop) {
+    if (pos >= stop) {   // (an empty chunk: still leave a defined pending word)
+        smem_st_u32(R, 0u, arena);
+        return 0u;
+    }
+    uint32_t np1, e1, e2;
+    do {
         const uint32_t win = funnel_l(w1, w0, pos);   // next 32 stream bits
-        uint32_t e1 = T.lut[win >> T.idx_shift];
+        e1 = T.lut[win >> T.idx_shift];
         if (LONG) {
-            if ((e1 >> 16) == 0) e1 = resolve_long(win, T.lut_bits, T.lt, T.order);
+            if (e1 == 0) e1 = resolve_long(win, T.lut_bits, T.lt, T.order);
         }
-        const uint32_t b1 = byte2(e1);
-        uint32_t np = pos + b1;
-        const uint32_t win2 = win << b1;
-        uint32_t e2 = T.lut[win2 >> T.idx_shift];
+        const uint32_t win2 = funnel_l(0u, win, e1);  // win << length of step 1 (the entry's low 5 bits)
+        e2 = T.lut[win2 >> T.idx_shift];
         if (LONG) {
-            if ((e2 >> 16) == 0) e2 = resolve_long(win2, T.lut_bits, T.lt, T.order);
+            if (e2 == 0) e2 = resolve_long(win2, T.lut_bits, T.lt, T.order);
         }
-        if (np < stop) {
-            e = e2;
+        np1 = add_byte(e1, T.sel_len, pos);
+        const uint32_t np = add_byte(e2, T.sel_len, np1);
+        // pack: X = the symbols of both steps
+        uint32_t X;
+        if (LONG) {   // (a skip entry has no symbols: general form)
+            X = ((e1 >> 8) & 0xffffu) | (((e2 >> 8) & 0xffffu) << (e1 >> 24));
         } else {
-            e = e1;
-            e2 = 0;
+            X = byte_perm(e1, e2, (e1 >> 24) * T.pair_slope + kPairSelBase);
         }
-        np += byte2(e2);
-        // pack: X = the symbols of both steps, n8 = 8 * (pending + new) symbols
-        const uint32_t c1 = e1 >> 24;
-        const uint32_t X = (e1 & 0xffffu) | ((e2 & 0xffffu) << c1);
-        const uint32_t n8 = np8 + c1 + (e2 >> 24);
-        const uint32_t lo = P | (X << np8);
-        const uint32_t hi = funnel_l(X, 0u, np8);   // the bytes of X that did not fit into lo (0 when np8 == 0)
-        if (n8 >= 32u) {
-            smem_st_u32(R, lo, arena);
+        const uint32_t n8n = add_byte(e2, T.sel_cnt8, add_byte(e1, T.sel_cnt8, n8));
+        P += funnel_l(0u, X, n8);                 // X << (n8 & 31); the bytes are disjoint: an add (FMA pipe), not an or
+        const uint32_t hi = funnel_l(X, 0u, n8);  // the bytes of X that did not fit (0 when n8 & 31 == 0)
+#if defined(__CUDA_ARCH__)
+        // four symbols complete: store the word, keep the overflow (one predicate; the adds are multiply-adds by the
+        // opaque 1: FMA pipe)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 x;\n\t"
+            "xor.b32 x, %3, %4;\n\t"
+            "and.b32 x, x, 32;\n\t"
+            "setp.ne.u32 p, x, 0;\n\t"
+            "@p st.shared.u32 [%0], %1;\n\t"
+            "@p mad.lo.u32 %0, %5, %6, %0;\n\t"   // R += row bytes
+            "@p mad.lo.u32 %1, %2, %5, 0;\n\t"    // P = hi
+            "}"
+            : "+r"(R), "+r"(P)
+            : "r"(hi), "r"(n8n), "r"(n8), "r"(T.one), "n"(NT * 4)
+            : "memory");
+#else
+        if ((n8n ^ n8) & 32u) {
+            smem_st_u32(R, P, arena);
             R += NT * 4u;
             P = hi;
-        } else {
-            P = lo;
         }
-        np8 = n8 & 31u;
+#endif
+        n8 = n8n;
 #if defined(__CUDA_ARCH__)
         // Crossed a unit boundary: slide the window and fetch the word after it.  One asm block with its own predicate,
-        // so that the slide stays predicated moves (FMA pipe; the INT pipe bounds this loop) and the load writes w2 IN
+        // so that the slide stays predicated moves (FMA pipe; the ALU pipe bounds this loop) and the load writes w2 IN
         // PLACE: it is consumed by the next slide, at least two lookups later, so its latency never sits on the
         // loop-carried path and it costs a shared-memory wavefront once per unit instead of once per lookup.
         asm volatile(
@@ -205,11 +250,18 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
         }
 #endif
         pos = np;
-    }
+    } while (pos < stop);
     smem_st_u32(R, P, arena);   // the pending symbols (a word past the last full one: the staging rows allow for it)
-    uint32_t cnt = (((R - stage_addr) >> row_shift(NT)) << 2) + (np8 >> 3);
-    // the second symbol of the last lookup starts exactly at `stop`: it is the successor's first symbol
-    if (pos > stop && (e >> 24) == 16u) --cnt;
+    // Take off what the last pair decoded past `stop`: the whole second step if the first one already reached it, and
+    // the second symbol of the step that reached it if that symbol STARTS at `stop` (it is the successor's first one).
+    uint32_t last = e2, lastpos = pos;
+    if (np1 >= stop) {
+        n8 -= (e2 >> 24);
+        last = e1;
+        lastpos = np1;
+    }
+    uint32_t cnt = n8 >> 3;
+    if (lastpos > stop && (last >> 24) == 16u) --cnt;
     return cnt;
 }
 
@@ -324,7 +376,7 @@ HD_HD uint32_t sync_step(uint32_t win, uint32_t pos, const SyncLut &L) {
     uint32_t ent = L.lut[win >> L.idx_shift];
     if (LONG) {
         if (ent == 0) {
-            const uint32_t first = (resolve_long(win, L.lm, L.lt, L.order) >> 16) & 0xffu;
+            const uint32_t first = resolve_long(win, L.lm, L.lt, L.order) & 0xffu;
             ent = first | (first << 8);
         }
     }

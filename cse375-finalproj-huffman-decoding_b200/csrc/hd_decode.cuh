@@ -60,6 +60,7 @@ struct TileParams {
     uint64_t *count_out;         // optional: total symbols written
     uint32_t stage_rows;         // rows of one staging buffer (one 32-bit word per lane each)
     uint32_t n_warps;            // decode warps per CTA (blockDim.x == (n_warps + 1) * 32)
+    uint32_t k_one, k_sel_len, k_sel_cnt8, k_pair_slope;   // 1, kSelLen, kSelCnt8, kPairSelSlope (see decode_chunk)
 };
 
 constexpr uint32_t kWarpRowBytes = 128;   // one row of a warp block: 32 lanes x 4 bytes
@@ -206,7 +207,12 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
     T.lut = s_lut;
     T.idx_shift = 32 - lm;
     T.lut_bits = lm;
-    T.one = lm != 0xffffffffu;   // 1 for every real table; ptxas cannot fold it
+    // constants of the decode loop come in as kernel parameters: opaque to ptxas, so they stay constant-bank operands
+    // instead of being re-materialised inside the loop (or, for `one`, folded into selects on the ALU pipe)
+    T.one = p.k_one;
+    T.sel_len = p.k_sel_len;
+    T.sel_cnt8 = p.k_sel_cnt8;
+    T.pair_slope = p.k_pair_slope;
     T.len_tab = nullptr;
     T.lt = s_long;
     T.order = s_order;

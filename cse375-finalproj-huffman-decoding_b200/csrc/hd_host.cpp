@@ -91,7 +91,12 @@ void build_table_blob(const HostCode &c, TableBlob &blob) {
     blob.lut_bits = lm;
     blob.min_len = c.min_len;
     blob.max_len = maxl;
-    blob.has_long = maxl > lm ? 1u : 0u;
+    // The resolver (LONG kernel variants) is needed for codes longer than the primary LUT, and for INCOMPLETE codes:
+    // their LUT has holes (windows that match no codeword), which the fast variants' symbol merge does not handle.
+    uint64_t kraft = 0;
+    for (int s = 0; s < 256; ++s)
+        if (c.len[s]) kraft += 1ull << (kMaxCodeLen - c.len[s]);
+    blob.has_long = (maxl > lm || kraft != (1ull << kMaxCodeLen)) ? 1u : 0u;
 
     // full-width helper table on the host: index = next maxl bits
     std::vector<uint16_t> flat((size_t)1 << maxl, 0);   // len<<8 | sym, 0 = hole
@@ -127,23 +132,19 @@ void build_table_blob(const HostCode &c, TableBlob &blob) {
     for (uint32_t w = 0; w < n; ++w) {
         uint32_t len0, sym0;
         if (!first_code(w, 0, len0, sym0)) {
-            if (blob.has_long) {
-                dec[w] = 0;            // meta 0 -> slow path resolves (or skips 1 bit)
-                syn[w] = 0;
-            } else {
-                dec[w] = 1u << 16;     // hole: consume one bit, emit nothing
-                syn[w] = (uint16_t)(1u | (1u << 8));
-            }
+            dec[w] = 0;                // (has_long is set) -> resolve_long finds the long codeword or skips 1 bit
+            syn[w] = 0;
             continue;
         }
-        uint32_t bits = len0, count = 1, syms = sym0;
-        uint32_t len1, sym1;
+        uint32_t bits = len0, count = 1;
+        uint32_t len1, sym1 = 0;
         if (first_code(w, bits, len1, sym1)) {
-            syms |= sym1 << 8;
             bits += len1;
             count = 2;
+        } else {
+            sym1 = 0;
         }
-        dec[w] = syms | (bits << 16) | (count << 27);   // top byte = 8 * count (decode_chunk packs with it)
+        dec[w] = lut_entry(bits, sym0, sym1, count);
         // sync: jump over every complete code in the window
         uint32_t jump = len0, l, s;
         while (jump < lm && first_code(w, jump, l, s)) jump += l;

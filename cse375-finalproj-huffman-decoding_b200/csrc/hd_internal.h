@@ -48,6 +48,17 @@ constexpr uint32_t sync_phys_unit(uint32_t i) {
                                    ((i - kSyncHaloSegs) % kSyncChunkSegs);
 }
 
+// Primary LUT entry: byte 0 = total length in bits of the entry's codewords (1..16: bits 5-7 are zero, so the ENTRY
+// ITSELF serves as a wrapping funnel-shift amount), byte 1 = first symbol, byte 2 = second symbol (0 if there is
+// none), byte 3 = 8 * number of symbols.  The byte fields are added up with dp4a (FMA pipe) instead of being
+// extracted with shifts (ALU pipe: the pipe that bounds the decode loop).  0 = "ask resolve_long" (LONG tables only).
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr uint32_t lut_entry(uint32_t len, uint32_t sym0, uint32_t sym1, uint32_t count) {
+    return len | (sym0 << 8) | (sym1 << 16) | (count << 27);
+}
+
 // Host description of a prefix code: code/len indexed by symbol value.
 struct HostCode {
     uint32_t code[256];
@@ -70,7 +81,7 @@ struct LongTables {
 };
 
 // All tables the kernels consume, laid out in ONE device blob:
-//   [0]                      u32 dec_lut[1<<lut_bits]   {sym0,sym1,bits|count<<8}
+//   [0]                      u32 dec_lut[1<<lut_bits]   lut_entry(): {bits, sym0, sym1, 8 * count}
 //   [off_sync]               u16 sync_lut[1<<lut_bits]  {jump_bits, first_len}
 //   [off_len]                u8  len_tab[256]
 //   [off_order]              u8  order[256]

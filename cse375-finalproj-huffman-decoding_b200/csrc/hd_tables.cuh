@@ -13,11 +13,12 @@
 
 namespace hd {
 
-struct TableSummary {      // read back by the host (16 bytes): everything it needs to launch the decode kernels
+struct TableSummary {      // read back by the host (20 bytes): everything it needs to launch the decode kernels
     uint32_t ok;           // 0 = malformed list
     uint32_t lut_bits;
     uint32_t min_len;
     uint32_t max_len;
+    uint32_t has_long;     // codes longer than the LUT, or an incomplete code: the kernels need the resolver
 };
 
 constexpr uint32_t kTableBlobMaxBytes = (4u << kMaxLutBits) + (2u << kMaxLutBits) + 256 + 256 + ((sizeof(LongTables) + 15) & ~15u);
@@ -74,11 +75,12 @@ __global__ void __launch_bounds__(1024) hd_build_tables_kernel(const hd_sym_len 
         s_lm = lm;
         s_min = min_len;
         s_max = max_len;
-        s_long = max_len > lm ? 1u : 0u;
+        s_long = (max_len > lm || code != (1ull << max_len)) ? 1u : 0u;   // long codes, or an incomplete code (LUT holes)
         summary->ok = s_ok;
         summary->lut_bits = lm;
         summary->min_len = min_len;
         summary->max_len = max_len;
+        summary->has_long = s_long;
     }
     __syncthreads();
     if (!s_ok) return;
@@ -89,17 +91,18 @@ __global__ void __launch_bounds__(1024) hd_build_tables_kernel(const hd_sym_len 
     for (uint32_t w = t; w < n; w += blockDim.x) {
         uint32_t len0, sym0;
         if (!table_first_code(w, 0, lm, lt, s_order, max_len, len0, sym0)) {
-            if (s_long) { dec[w] = 0; syn[w] = 0; }                                    // slow path resolves (or skips 1 bit)
-            else { dec[w] = 1u << 16; syn[w] = (uint16_t)(1u | (1u << 8)); }           // hole: consume one bit, emit nothing
+            dec[w] = 0;   // (s_long is set) -> resolve_long finds the long codeword or skips 1 bit
+            syn[w] = 0;
             continue;
         }
-        uint32_t bits = len0, count = 1, syms = sym0, len1, sym1;
+        uint32_t bits = len0, count = 1, len1, sym1 = 0;
         if (table_first_code(w, bits, lm, lt, s_order, max_len, len1, sym1)) {
-            syms |= sym1 << 8;
             bits += len1;
             count = 2;
+        } else {
+            sym1 = 0;
         }
-        dec[w] = syms | (bits << 16) | (count << 27);   // top byte = 8 * count
+        dec[w] = lut_entry(bits, sym0, sym1, count);
         uint32_t jump = len0, l, s;
         while (jump < lm && table_first_code(w, jump, lm, lt, s_order, max_len, l, s)) jump += l;
         syn[w] = (uint16_t)(jump | (len0 << 8));

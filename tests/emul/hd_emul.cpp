@@ -29,6 +29,9 @@ void bind(HostTables &h) {
     h.T.idx_shift = 32 - h.blob.lut_bits;
     h.T.lut_bits = h.blob.lut_bits;
     h.T.one = 1;
+    h.T.sel_len = hd::kSelLen;
+    h.T.sel_cnt8 = hd::kSelCnt8;
+    h.T.pair_slope = hd::kPairSelSlope;
     h.T.len_tab = b + h.blob.off_len;
     h.T.order = b + h.blob.off_order;
     h.T.lt = reinterpret_cast<const LongTables *>(b + h.blob.off_long);
