@@ -174,7 +174,9 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
             const uint64_t agg = __shfl_sync(0xffffffffu, wi, 31);
             // (the tile AGGREGATE was already published by the last decode warp to finish; tile 0 published its PREFIX)
             uint64_t excl = 0;
-            if (tile > 0) {
+            if (HD_WHATIF & 1) {
+                excl = tile * agg;   // (timing experiment: no look-back)
+            } else if (tile > 0) {
                 excl = lookback_wide(p.tile_status, tile, lane, p.tile_counter + 1);
                 if (lane == 0) red_max_gpu_u64(p.tile_status + tile * kStatusStride, kFlagPrefix | (excl + agg));
             }
@@ -315,7 +317,8 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
                 }
                 smem_st_u32(col_abs + (4 * SEGS + 0) * kWarpRowBytes, pf_la.x, nullptr);
                 smem_st_u32(col_abs + (4 * SEGS + 1) * kWarpRowBytes, pf_la.y, nullptr);
-                cnt = decode_chunk<32, LONG>(col, pf_entry, pf_stop, T, stage0_abs + b * stage_bytes + lane * 4u, nullptr);
+                if (HD_WHATIF & 4) cnt = 43u;   // (timing experiment: no decode loop)
+                else cnt = decode_chunk<32, LONG>(col, pf_entry, pf_stop, T, stage0_abs + b * stage_bytes + lane * 4u, nullptr);
             }
             // ---------------- warp-wide inclusive scan of the counts ----------------
             incl = cnt;
@@ -366,12 +369,14 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
             uint32_t w[RCAP + 2];
 #pragma unroll
             for (int i = 0; i < RCAP + 2; ++i) w[i] = 0;
-            column_read<RCAP>(sblk + lane * 4u, rows_max, w, nullptr);
-            __syncwarp();
             const uint32_t D = sblk + phase + excl_l;
-            column_write<RCAP>(w, c, D, rows_max, nullptr);
-            __syncwarp();
-            column_write_head(w[0], c, D, nullptr);
+            if (!(HD_WHATIF & 2)) {   // (timing experiment: no compaction)
+                column_read<RCAP>(sblk + lane * 4u, rows_max, w, nullptr);
+                __syncwarp();
+                column_write<RCAP>(w, c, D, rows_max, nullptr);
+                __syncwarp();
+                column_write_head(w[0], c, D, nullptr);
+            }
             fence_proxy_async_smem();
             __syncwarp();
             // flush: the warp's span is contiguous in the block and in the output, and both have the same 16-byte
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
             if (head > total) head = total;
             const uint32_t body = (total - head) & ~15u;
             const uint32_t tail = total - head - body;
-            if (body) {   // (warp-uniform)
+            if (body && !(HD_WHATIF & 8)) {   // (warp-uniform; timing experiment 8: no flush)
                 if (lane == 0) {
                     tma_bulk_store_s(gp + head, sp + head, body);
                     tma_bulk_commit();
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
                 store_pending |= 1u << pb;
             }
             const uint32_t hb = lane < 16 ? lane : head + body + lane - 16u;   // byte of the span this lane may copy
-            if (lane < 16 ? lane < head : lane - 16u < tail) gp[hb] = (uint8_t)smem_ld_u8(sp + hb);
+            if (!(HD_WHATIF & 8) && (lane < 16 ? lane < head : lane - 16u < tail)) gp[hb] = (uint8_t)smem_ld_u8(sp + hb);
         }
         if (!valid) break;
         prev_valid = true;
