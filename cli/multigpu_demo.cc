@@ -2,9 +2,10 @@
 // CLI shape and timer lines of the reference's multi-GPU demo (gpuhd/multigpu_demo.cc:56-75, 141, 159, 176, 293, 300,
 // 325-332), written fresh.  The reference slices compressed units AND symbols into equal 1/n parts, which cannot work
 // (README.md:37 "TESTS FAIL"); here the stream is cut on 128-bit subsequence boundaries, every GPU decodes its shard
-// (plus a left halo it parses speculatively) independently from its own HBM with hd_decode_selfsync_shard, and the
-// only exchange is an NCCL all-gather of {symbols decoded, entry offset, exit offset} per GPU over NVLink; the
-// exclusive scan of the counts places the outputs in the host vector.
+// (plus a left halo it parses speculatively) independently from its own HBM, and the only exchange is an NCCL
+// all-gather of {symbols decoded, entry offset, exit offset} per GPU over NVLink; the exclusive scan of the counts
+// places the outputs in the host vector.  Plan, decode + exchange, seam repair and placement are the library's
+// hd_mgpu_* layer (include/hd_b200.h): this file only allocates, uploads and downloads.
 #include <cuhd.h>
 #include <llhuff.h>
 #include <nccl.h>
@@ -16,15 +17,13 @@
 #include <vector>
 
 #define INPUT_FILENAME "../input_data.bin"
-static const uint64_t kHaloSegments = 4096;   // 64 KiB of stream, >> self-synchronisation distance
 
 struct Shard {
-    uint64_t seg_begin = 0, seg_end = 0, halo_units = 0, shard_units = 0, readable_units = 0, first_unit = 0;
+    hd_mgpu_plan plan;
+    hd_mgpu *ctx = nullptr;
     uint32_t *d_units = nullptr;
     uint8_t *d_out = nullptr;
     void *d_ws = nullptr;
-    size_t ws_bytes = 0, out_cap = 0;
-    uint64_t *d_info = nullptr, *d_all = nullptr;
     hd_table *table = nullptr;
     cudaStream_t stream = nullptr;
     uint64_t offset = 0, count = 0;
@@ -82,7 +81,6 @@ int main(int argc, char **argv) {
                                  enc_table->compressed_size * sizeof(UNIT_TYPE));
     const UNIT_TYPE *units = in_buf.get_compressed_data();
     const uint64_t n_units = in_buf.get_compressed_size_units();
-    const uint64_t n_seg = SDIV(n_units, 4);
     uint32_t min_len = 16;
     for (auto &p : enc_table->pairs) min_len = std::min<uint32_t>(min_len, p.length);
 
@@ -95,74 +93,42 @@ int main(int argc, char **argv) {
         for (int g = 0; g < n_gpus; ++g) {
             Shard &s = shards[g];
             CUHD_CHECK(cudaSetDevice(g));
-            hd_shard_segments(n_seg, (uint32_t)g, (uint32_t)n_gpus, &s.seg_begin, &s.seg_end);
-            const uint64_t halo = g ? std::min<uint64_t>(kHaloSegments, s.seg_begin) / 8 * 8 : 0;
-            s.first_unit = (s.seg_begin - halo) * 4;
-            const uint64_t end_unit = std::min<uint64_t>(s.seg_end * 4, n_units);
-            s.halo_units = halo * 4;
-            s.shard_units = end_unit - s.seg_begin * 4;
-            s.readable_units = std::min<uint64_t>(end_unit + 4, n_units) - s.first_unit;
-            s.out_cap = (size_t)(s.shard_units * 32 / min_len + 64);
-            s.ws_bytes = hd_workspace_bytes_selfsync(s.halo_units + s.shard_units);
+            cuhd::cuhd_check_hd(hd_mgpu_plan_shard(HD_SCHEME_SELFSYNC, n_units, (uint32_t)g, (uint32_t)n_gpus, min_len, 0,
+                                                   &s.plan), "hd_mgpu_plan_shard");
             CUHD_CHECK(cudaStreamCreate(&s.stream));
-            CUHD_CHECK(cudaMalloc(reinterpret_cast<void **>(&s.d_units), s.readable_units * 4 + 16));
-            CUHD_CHECK(cudaMalloc(reinterpret_cast<void **>(&s.d_out), s.out_cap));
-            CUHD_CHECK(cudaMalloc(&s.d_ws, s.ws_bytes));
-            CUHD_CHECK(cudaMalloc(reinterpret_cast<void **>(&s.d_info), 3 * sizeof(uint64_t)));
-            CUHD_CHECK(cudaMalloc(reinterpret_cast<void **>(&s.d_all), 3 * sizeof(uint64_t) * n_gpus));
+            CUHD_CHECK(cudaMalloc(reinterpret_cast<void **>(&s.d_units), s.plan.readable_units * 4 + 16));
+            CUHD_CHECK(cudaMalloc(reinterpret_cast<void **>(&s.d_out), s.plan.out_capacity + 64));
+            CUHD_CHECK(cudaMalloc(&s.d_ws, s.plan.workspace_bytes + 64));
             cuhd::cuhd_check_hd(hd_table_from_flat_lut(reinterpret_cast<const hd_lut_entry *>(dec_table->get()),
                                                        MAX_CODEWORD_LENGTH, s.stream, &s.table),
                                 "hd_table_from_flat_lut");
-            CUHD_CHECK(cudaMemcpyAsync(s.d_units, units + s.first_unit, s.readable_units * 4, cudaMemcpyHostToDevice,
+            cuhd::cuhd_check_hd(hd_mgpu_create(HD_SCHEME_SELFSYNC, (uint32_t)g, (uint32_t)n_gpus, &s.plan, &s.ctx), "hd_mgpu_create");
+            if (n_gpus > 1) cuhd::cuhd_check_hd(hd_mgpu_exchange_nccl(s.ctx, comms[g]), "hd_mgpu_exchange_nccl");
+            cuhd::cuhd_check_hd(hd_mgpu_bind(s.ctx, s.d_units, nullptr, s.table, s.d_out, s.d_ws), "hd_mgpu_bind");
+            CUHD_CHECK(cudaMemcpyAsync(s.d_units, units + s.plan.first_unit, s.plan.readable_units * 4, cudaMemcpyHostToDevice,
                                        s.stream));
         }
         for (int g = 0; g < n_gpus; ++g) { CUHD_CHECK(cudaSetDevice(g)); CUHD_CHECK(cudaStreamSynchronize(shards[g].stream)); }
     TIMER_STOP
 
-    std::vector<uint64_t> infos(3 * (size_t)n_gpus);
     TIMER_START(timings, "Multi-GPU Parallel Decode Time (Full Span)")
-        // one host thread per GPU: the decode call reads one 4-byte convergence flag per shard (a host sync)
+        // one host thread per GPU (the shape of one process per GPU): shard decode + all-gather of the three integers on
+        // the stream, then the collective host half (convergence flag, seam check / repair, output placement)
         std::vector<std::thread> th;
         for (int g = 0; g < n_gpus; ++g)
             th.emplace_back([&, g]() {
                 Shard &s = shards[g];
                 CUHD_CHECK(cudaSetDevice(g));
-                cuhd::cuhd_check_hd(hd_decode_selfsync_shard(s.d_units, s.halo_units, s.shard_units, s.readable_units, 0,
-                                                             s.table, s.d_out, s.out_cap, s.d_ws, s.ws_bytes, s.d_info,
-                                                             s.stream),
-                                    "hd_decode_selfsync_shard");
+                cuhd::cuhd_check_hd(hd_mgpu_enqueue(s.ctx, s.stream), "hd_mgpu_enqueue");
+                cuhd::cuhd_check_hd(hd_mgpu_finish(s.ctx, size, &s.offset, &s.count, s.stream), "hd_mgpu_finish");
             });
         for (auto &t : th) t.join();
-        NCCL_CHECK(ncclGroupStart());
-        for (int g = 0; g < n_gpus; ++g)
-            NCCL_CHECK(ncclAllGather(shards[g].d_info, shards[g].d_all, 3, ncclUint64, comms[g], shards[g].stream));
-        NCCL_CHECK(ncclGroupEnd());
-        for (int g = 0; g < n_gpus; ++g) { CUHD_CHECK(cudaSetDevice(g)); CUHD_CHECK(cudaStreamSynchronize(shards[g].stream)); }
-        CUHD_CHECK(cudaSetDevice(0));
-        CUHD_CHECK(cudaMemcpy(infos.data(), shards[0].d_all, infos.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        // seam check: entry of shard g == exit of shard g-1; a shard whose halo was too short is re-decoded from the
-        // exact offset (sequential chain in the worst case)
-        for (int g = 1; g < n_gpus; ++g) {
-            if (infos[3 * g + 1] == infos[3 * (g - 1) + 2]) continue;
-            Shard &s = shards[g];
-            CUHD_CHECK(cudaSetDevice(g));
-            cuhd::cuhd_check_hd(hd_decode_selfsync_shard(s.d_units + s.halo_units, 0, s.shard_units,
-                                                         s.readable_units - s.halo_units,
-                                                         (uint32_t)infos[3 * (g - 1) + 2], s.table, s.d_out, s.out_cap,
-                                                         s.d_ws, s.ws_bytes, s.d_info, s.stream),
-                                "hd_decode_selfsync_shard (repair)");
-            CUHD_CHECK(cudaMemcpy(&infos[3 * g], s.d_info, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        }
     TIMER_STOP
 
     std::vector<SYMBOL_TYPE> decoded(size);
     TIMER_START(timings, "Multi-GPU Memcpy DtH & Combine")
-        uint64_t off = 0;
         for (int g = 0; g < n_gpus; ++g) {
             Shard &s = shards[g];
-            s.offset = off;
-            s.count = off >= size ? 0 : std::min<uint64_t>(infos[3 * g], size - off);
-            off += infos[3 * g];
             CUHD_CHECK(cudaSetDevice(g));
             CUHD_CHECK(cudaMemcpyAsync(decoded.data() + s.offset, s.d_out, s.count, cudaMemcpyDeviceToHost, s.stream));
         }
@@ -174,6 +140,7 @@ int main(int argc, char **argv) {
     if (!cuhd::CUHDUtil::equals(buffer.data(), decoded.data(), size)) std::cout << "mismatch" << std::endl;
     for (int g = 0; g < n_gpus; ++g) {
         cudaSetDevice(g);
+        hd_mgpu_destroy(shards[g].ctx);
         hd_table_free(shards[g].table);
         ncclCommDestroy(comms[g]);
     }

@@ -53,7 +53,10 @@ ABI_SYMBOLS = [
     "hd_decode_selfsync_shard_enqueue", "hd_decode_selfsync_shard_finish", "hd_workspace_bytes_encode",
     "hd_histogram_device", "hd_build_code_from_histogram", "hd_encode_device", "hd_mailbox_create",
     "hd_mailbox_export", "hd_mailbox_connect", "hd_mailbox_publish", "hd_mailbox_wait", "hd_mailbox_timed_out",
-    "hd_mailbox_destroy",
+    "hd_mailbox_destroy", "hd_decode_gap_shard", "hd_mgpu_plan_shard", "hd_mgpu_first_bad_seam", "hd_mgpu_place",
+    "hd_mgpu_create", "hd_mgpu_destroy", "hd_mgpu_exchange_mailbox", "hd_mgpu_exchange_nccl",
+    "hd_mgpu_exchange_callback", "hd_mgpu_bind", "hd_mgpu_enqueue", "hd_mgpu_align", "hd_mgpu_finish", "hd_mgpu_infos",
+    "hd_mgpu_repair_count",
 ]
 PROFILE_SLOTS = ("sync_chunks", "sync_seams", "decode_write", "reserved")
 
@@ -136,6 +139,25 @@ def lib():
     L.hd_decode_selfsync_shard.argtypes = [vp, u64, u64, u64, u32, vp, vp, u64, vp, sz, vp, vp]
     L.hd_decode_selfsync_shard_enqueue.argtypes = [vp, u64, u64, u64, u32, vp, vp, u64, vp, sz, vp, vp, vp]
     L.hd_decode_selfsync_shard_finish.argtypes = [vp, u64, u64, u64, u32, vp, vp, u64, vp, sz, vp, vp, vp]
+    L.hd_decode_gap_shard.argtypes = [vp, u64, vp, u64, C.c_int, vp, vp, u64, vp, sz, vp, vp]
+    L.hd_mgpu_plan_shard.argtypes = [C.c_int, u64, u32, u32, u32, u64, vp]
+    L.hd_mgpu_first_bad_seam.argtypes = [vp, u32]
+    L.hd_mgpu_first_bad_seam.restype = u32
+    L.hd_mgpu_place.argtypes = [vp, u32, u64, u32, C.POINTER(u64), C.POINTER(u64)]
+    L.hd_mgpu_place.restype = None
+    L.hd_mgpu_create.argtypes = [C.c_int, u32, u32, vp, C.POINTER(vp)]
+    L.hd_mgpu_destroy.argtypes = [vp]
+    L.hd_mgpu_destroy.restype = None
+    L.hd_mgpu_exchange_mailbox.argtypes = [vp, vp]
+    L.hd_mgpu_exchange_nccl.argtypes = [vp, vp]
+    L.hd_mgpu_exchange_callback.argtypes = [vp, vp, vp]
+    L.hd_mgpu_bind.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.hd_mgpu_enqueue.argtypes = [vp, vp]
+    L.hd_mgpu_align.argtypes = [vp, vp]
+    L.hd_mgpu_finish.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(u64), vp]
+    L.hd_mgpu_infos.argtypes = [vp, vp]
+    L.hd_mgpu_repair_count.argtypes = [vp]
+    L.hd_mgpu_repair_count.restype = u32
     _lib = L
     return L
 
@@ -465,7 +487,8 @@ def launch_count():
     return int(lib().hd_launch_count())
 
 
-from .sharding import ShardedSelfSyncDecoder, plan_shards, place_outputs, seams_ok, resolve_seams  # noqa: E402
+from .sharding import (ShardedSelfSyncDecoder, ShardedGapDecoder, plan_shard, plan_shards, place_outputs, seams_ok,  # noqa: E402
+                       resolve_seams, SCHEME_SELFSYNC, SCHEME_GAP)
 
 
 def encode_device(d_data, max_len, pad_unit=False):

@@ -233,7 +233,8 @@ hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32
                          uint64_t n_symbols, const Workspace &w, uint64_t *d_count, cudaStream_t s,
                          uint64_t n_units_readable = 0, const uint32_t *entry_word = nullptr,
                          uint64_t *shard_info = nullptr, bool already_zeroed = false,
-                         const uint64_t *d_off_in = nullptr, uint64_t *d_off_out = nullptr) {
+                         const uint64_t *d_off_in = nullptr, uint64_t *d_off_out = nullptr,
+                         const uint32_t *unconverged = nullptr) {
     TileGeom g;
     if (!pick_tile_geom(table, device_info().max_smem_optin, g)) return HD_ERR_INVALID;
     TileParams q;
@@ -244,6 +245,7 @@ hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32
     q.first_bit = first_bit;
     q.entry_word = entry_word;
     q.shard_info = shard_info;
+    q.unconverged = unconverged;
     q.table = table_dev(table);
     q.out = d_out;
     q.n_symbols = n_symbols;
@@ -513,6 +515,23 @@ hd_status hd_decode_gap_ex(const uint32_t *d_units, uint64_t n_units, const uint
                           d_count, static_cast<cudaStream_t>(stream));
 }
 
+// One shard of a gap-array stream (multi-GPU).  d_gap_words[-1] must be readable when d_entry_from_prev is set: its top
+// nibble is the offset at which the shard's first segment starts (decoder.cu:505-507).
+hd_status hd_decode_gap_shard(const uint32_t *d_units, uint64_t n_units_readable, const uint32_t *d_gap_words,
+                              uint64_t n_segments, int entry_from_prev_word, const hd_table *table, uint8_t *d_out,
+                              uint64_t out_cap, void *d_workspace, size_t workspace_bytes, uint64_t *d_shard_info,
+                              void *stream) {
+    hd_status st = check_common(d_units, n_units_readable, table, d_out, out_cap, d_workspace);
+    if (st != HD_OK) return st;
+    if (n_units_readable == 0 || n_segments == 0 || n_segments > div_up(n_units_readable, kSegmentUnits) || !d_gap_words)
+        return HD_ERR_INVALID;
+    if (workspace_bytes < ws_bytes(n_units_readable, false)) return HD_ERR_WORKSPACE;
+    Workspace w = carve(d_workspace, n_units_readable, false);
+    return run_gap_decode(d_units, n_units_readable, d_gap_words, n_segments, 0, table, d_out, out_cap, w, nullptr,
+                          static_cast<cudaStream_t>(stream), 0, entry_from_prev_word ? d_gap_words - 1 : nullptr,
+                          d_shard_info);
+}
+
 hd_status hd_decode_gap(const uint32_t *d_units, uint64_t n_units, const uint32_t *d_gap_words,
                         uint64_t n_segments, const hd_table *table, uint8_t *d_out, uint64_t n_symbols,
                         void *d_workspace, size_t workspace_bytes, void *stream) {
@@ -631,12 +650,16 @@ static hd_status shard_args(const uint32_t *d_units, uint64_t n_units_halo, uint
 static hd_status shard_decode(const uint32_t *d_units, uint64_t n_units_halo, uint64_t n_units_shard,
                               uint64_t n_units_readable, uint32_t first_bit, const hd_table *table, uint8_t *d_out,
                               uint64_t out_cap, const Workspace &w, uint64_t *d_shard_info, cudaStream_t s,
-                              bool already_zeroed, const uint64_t *d_off_in = nullptr, uint64_t *d_off_out = nullptr) {
+                              bool already_zeroed, const uint64_t *d_off_in = nullptr, uint64_t *d_off_out = nullptr,
+                              bool speculative = false) {
     const uint64_t halo_words = n_units_halo / (kSegmentUnits * 8);
     const uint32_t *gaps = w.gap_words + halo_words;
+    // speculative = decoded before the convergence counter of the synchronisation has been looked at: the counter is
+    // folded into the published triple so that every rank of a sharded decode learns that this shard is decoded again
     return run_gap_decode(d_units + n_units_halo, n_units_shard, gaps, div_up(n_units_shard, kSegmentUnits), first_bit,
                           table, d_out, out_cap, w, nullptr, s, n_units_readable - n_units_halo,
-                          n_units_halo ? gaps - 1 : nullptr, d_shard_info, already_zeroed, d_off_in, d_off_out);
+                          n_units_halo ? gaps - 1 : nullptr, d_shard_info, already_zeroed, d_off_in, d_off_out,
+                          speculative ? w.changed : nullptr);
 }
 
 // asynchronous half (see hd_decode_selfsync_enqueue); d_off_in / d_off_out chain the output position of consecutive
@@ -660,7 +683,7 @@ static hd_status shard_enqueue_impl(const uint32_t *d_units, uint64_t n_units_ha
     st = run_sync(L, s);
     if (st != HD_OK) return st;
     st = shard_decode(d_units, n_units_halo, n_units_shard, n_units_readable, first_bit, table, d_out, out_cap, w,
-                      d_shard_info, s, true, d_off_in, d_off_out);
+                      d_shard_info, s, true, d_off_in, d_off_out, true);
     if (st != HD_OK) return st;
     if (L.p.n_chunks > 1) HD_CUDA(cudaMemcpyAsync(h_unconverged, w.changed, 4, cudaMemcpyDeviceToHost, s));
     return HD_OK;

@@ -48,7 +48,8 @@ struct TileParams {
     uint64_t n_segments;         // segments to DECODE
     uint32_t first_bit;          // start offset of segment 0 ...
     const uint32_t *entry_word;  // ... unless set: start offset of segment 0 = *entry_word >> 28
-    uint64_t *shard_info;        // optional {count, entry_bit, exit_bit} for the multi-GPU seam check
+    uint64_t *shard_info;        // optional {count, entry_bit | unconverged << 32, exit_bit} for the multi-GPU seam check
+    const uint32_t *unconverged; // optional: the self-sync pass's "an exit moved after it was published" counter
     TableDev table;
     uint8_t *out;
     uint64_t n_symbols;
@@ -191,7 +192,10 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
                     if (p.out_offset_out) *p.out_offset_out = out_off + tot;
                     if (p.shard_info) {
                         p.shard_info[0] = tot;
-                        p.shard_info[1] = p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit;
+                        // (the counter was written by the synchronisation kernel, earlier on this stream; nonzero = the
+                        // decode has to be repeated after the K1b rounds: every rank sees that in the exchanged triple)
+                        const uint64_t unconv = (p.unconverged && *reinterpret_cast<const volatile uint32_t *>(p.unconverged)) ? 1ull << 32 : 0ull;
+                        p.shard_info[1] = (uint64_t)(p.entry_word ? (__ldg(p.entry_word) >> 28) : p.first_bit) | unconv;
                         p.shard_info[2] = gap_nibble(p.gap_words, p.n_segments - 1);   // where the parse leaves the shard
                     }
                 }

@@ -1,15 +1,17 @@
-"""Multi-GPU sharding of ONE Huffman stream (one process per GPU, torch.distributed for the plumbing).
+"""Multi-GPU sharding of ONE Huffman stream: thin Python callers of the C ABI's hd_mgpu_* layer (one process per GPU,
+torch.distributed only for the set-up plumbing).
 
 Replaces gpuhd/multigpu_demo.cc:178-227,255-313, which slices the compressed units AND the symbols into equal 1/n
-parts (wrong by construction: the reference README says "MULTI-GPU BUT TESTS FAIL", README.md:37).  Here the stream
-is cut on 128-bit subsequence boundaries (whole 256-segment tiles); every rank decodes its shard independently from
-local HBM and the only exchange is an all-gather of three integers per rank:
+parts (wrong by construction: the reference README says "MULTI-GPU BUT TESTS FAIL", README.md:37).  The shard plan,
+the decode + exchange step, the seam protocol and the output placement all live in the library
+(csrc/hd_mgpu.cu): the stream is cut on 128-bit subsequence boundaries (whole 256-segment tiles), every rank decodes
+its shard independently from local HBM, and the only exchange is three integers per rank
 
     {symbols decoded, entry bit offset assumed, bit offset at which the parse leaves the shard}
 
 entry[g] must equal exit[g-1] (it does once the left halo is longer than the self-synchronisation distance; a
-mismatching rank re-decodes from the exact offset), and the exclusive scan of the counts places the outputs.
-The decode itself is pluggable so that the host logic is testable on CPU with the gloo backend.
+mismatching rank decodes again from the exact offset), and the exclusive scan of the counts places the outputs.
+Both schemes: ShardedSelfSyncDecoder (gpuhd streams) and ShardedGapDecoder (.huff gap arrays, no halo, no repair).
 """
 import ctypes as C
 
@@ -17,106 +19,129 @@ import numpy as np
 
 HALO_SEGMENTS = 4096          # left halo: 4096 x 128 bit = 64 KiB of stream (>> observed max sync distance ~5 Kbit)
 SEGMENT_UNITS = 4
-TILE_SEGMENTS = 256
+SCHEME_SELFSYNC, SCHEME_GAP = 0, 1
+EMPTY = (1 << 64) - 1
+
+
+class MgpuPlan(C.Structure):
+    """== hd_mgpu_plan (include/hd_b200.h)"""
+    _fields_ = [(n, C.c_uint64) for n in ("seg_begin", "seg_end", "first_unit", "halo_units", "shard_units",
+                                          "readable_units", "first_gap_word", "n_gap_words", "out_capacity",
+                                          "workspace_bytes")]
+
+
+def _lib():
+    from . import lib
+    return lib()
+
+
+def plan_shard(scheme, n_units, rank, world, min_code_length=1, halo_segments=0):
+    """hd_mgpu_plan_shard: what rank `rank` of `world` uploads and decodes."""
+    from . import _check
+    p = MgpuPlan()
+    _check(_lib().hd_mgpu_plan_shard(scheme, n_units, rank, world, min_code_length, halo_segments, C.byref(p)),
+           "hd_mgpu_plan_shard")
+    return p
 
 
 def plan_shards(n_units, world, halo_segments=HALO_SEGMENTS):
-    """[(seg_begin, seg_end, halo_segments)] per rank; boundaries are whole tiles (hd_shard_segments)."""
-    n_seg = (n_units + SEGMENT_UNITS - 1) // SEGMENT_UNITS
-    n_tiles = (n_seg + TILE_SEGMENTS - 1) // TILE_SEGMENTS
-    plan = []
+    """[(seg_begin, seg_end, halo_segments)] per rank of a self-sync decode (hd_mgpu_plan_shard)."""
+    res = []
     for r in range(world):
-        b = (n_tiles * r // world) * TILE_SEGMENTS
-        e = min((n_tiles * (r + 1) // world) * TILE_SEGMENTS, n_seg)
-        h = min(halo_segments, b) if r > 0 else 0
-        h -= h % 8
-        plan.append((b, e, h))
-    return plan
+        p = plan_shard(SCHEME_SELFSYNC, n_units, r, world, 1, halo_segments)
+        res.append((int(p.seg_begin), int(p.seg_end), int(p.halo_units) // SEGMENT_UNITS))
+    return res
+
+
+def _infos_array(infos):
+    rows = [[int(v) & EMPTY for v in row] for row in np.asarray(infos, dtype=object).reshape(-1, 3)]
+    return np.ascontiguousarray(np.array(rows, dtype=np.uint64))
 
 
 def place_outputs(counts, n_symbols):
-    """Exclusive scan of per-rank counts -> (offset, valid_count) per rank, clamped to the stream's symbol count
-    (the last shard also decodes the pad bits)."""
-    res, off = [], 0
-    for c in counts:
-        c = int(c)
-        valid = max(0, min(c, n_symbols - off))
-        res.append((off, valid))
-        off += c
+    """hd_mgpu_place for every rank: [(offset, valid_count)], clamped to the stream's symbol count."""
+    world = len(counts)
+    infos = np.zeros((world, 3), dtype=np.uint64)
+    infos[:, 0] = np.array([int(c) for c in counts], dtype=np.uint64)
+    res = []
+    off, cnt = C.c_uint64(0), C.c_uint64(0)
+    for r in range(world):
+        _lib().hd_mgpu_place(infos.ctypes.data, world, int(n_symbols), r, C.byref(off), C.byref(cnt))
+        res.append((int(off.value), int(cnt.value)))
     return res
 
 
 def seams_ok(infos):
-    """infos[g] = (count, entry, exit).  Returns the list of ranks whose assumed entry offset was wrong."""
+    """Ranks whose assumed entry offset was wrong given their predecessor's exit (repeated hd_mgpu_first_bad_seam)."""
+    a = _infos_array(infos)
+    world = len(a)
     bad = []
-    for g in range(1, len(infos)):
-        if int(infos[g][1]) != int(infos[g - 1][2]):
-            bad.append(g)
-    return bad
+    while True:
+        g = int(_lib().hd_mgpu_first_bad_seam(a.ctypes.data, world))
+        if g >= world:
+            return bad
+        bad.append(g)
+        # pretend the seam is repaired (entry := what the predecessor left) and look for the next one
+        prev = [k for k in range(g) if int(a[k, 1]) != EMPTY]
+        a[g, 1] = a[prev[-1], 2]
 
 
 def resolve_seams(rank, world, infos, gather, redecode, n_symbols):
-    """The seam protocol, independent of where the decode runs.  infos = gathered (count, entry, exit) rows;
-    gather() re-gathers after a repair; redecode(first_bit) re-decodes THIS rank's shard from an exact entry offset.
-    A wrong seam can only be repaired once its predecessor is right, so at most world-1 rounds (sequential chain,
-    the worst case of a code that never self-synchronises)."""
-    for _ in range(world):
-        bad = seams_ok(infos)
-        if not bad:
-            return place_outputs([row[0] for row in infos], n_symbols)
-        g = bad[0]
+    """The seam protocol of hd_mgpu_finish with a pluggable decode (host-logic tests on CPU / gloo): infos = gathered
+    (count, entry, exit) rows; gather() re-gathers after a repair; redecode(first_bit) decodes THIS rank's shard again
+    from an exact entry offset.  A wrong seam can only be repaired once its predecessor is right, so at most world-1
+    rounds (sequential chain: the worst case of a code that never self-synchronises)."""
+    L = _lib()
+    for _ in range(world + 1):
+        a = _infos_array(infos)
+        g = int(L.hd_mgpu_first_bad_seam(a.ctypes.data, world))
+        if g >= world:
+            return place_outputs([int(row[0]) for row in a], n_symbols)
         if rank == g:
-            redecode(int(infos[g - 1][2]))
+            prev = [k for k in range(g) if int(a[k, 1]) != EMPTY]
+            redecode(int(a[prev[-1], 2]) & 15)
         infos = gather()
     raise RuntimeError("shard seams did not converge")
 
 
-class ShardedSelfSyncDecoder:
-    """One rank's shard of a self-synchronising decode (CUDA)."""
+class _ShardedDecoder:
+    """One rank of a sharded decode: device buffers + an hd_mgpu context.  Subclasses upload their inputs."""
+    scheme = SCHEME_SELFSYNC
 
-
-    def __init__(self, units, table, n_symbols, rank, world, dist=None, halo_segments=HALO_SEGMENTS,
-                 use_mailbox=True):
+    def _setup(self, n_units, table, n_symbols, rank, world, dist, use_mailbox, halo_segments=0, allgather=None):
         import torch
         from . import lib, _check, _stream_ptr
         self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
         self._lib, self._check, self._stream_ptr = lib(), _check, _stream_ptr
         self.table = table
         self.n_symbols = int(n_symbols)
-        n_units = len(units)
-        self.plan = plan_shards(n_units, world, halo_segments)
-        b, e, h = self.plan[rank]
-        self.seg_begin, self.seg_end, self.halo = b, e, h
-        u0 = (b - h) * SEGMENT_UNITS
-        u1 = min(e * SEGMENT_UNITS, n_units)
-        u_read = min(u1 + SEGMENT_UNITS, n_units)            # right halo: the last codeword may end there
-        self.n_units_halo = h * SEGMENT_UNITS
-        self.n_units_local = u1 - b * SEGMENT_UNITS
-        self.n_units_readable = u_read - u0
-        self.h_units = np.array(units[u0:u_read], dtype=np.uint32)   # private, writable copy of the shard
-        self.d_units = torch.from_numpy(self.h_units.view(np.int32)).cuda()
-        min_len = max(1, table.min_length)
-        self.out_cap = (self.n_units_local * 32 + min_len - 1) // min_len + 64
+        self.plan = plan_shard(self.scheme, n_units, rank, world, max(1, table.min_length), halo_segments)
+        p = self.plan
+        self.n_units_local = int(p.shard_units)
+        self.out_cap = max(64, int(p.out_capacity))
         self.out = torch.empty(self.out_cap, dtype=torch.uint8, device="cuda")
-        nbytes = self._lib.hd_workspace_bytes_selfsync(self.n_units_halo + self.n_units_local)
-        self.ws = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
+        self.ws = torch.empty(int(p.workspace_bytes) + 128, dtype=torch.uint8, device="cuda")
         self.ws_ptr = self.ws.data_ptr() + (-self.ws.data_ptr()) % 64
-        self.ws_bytes = nbytes
-        self.info = torch.zeros(3, dtype=torch.int64, device="cuda")
-        self.all_info = torch.zeros(world * 3, dtype=torch.int64, device="cuda")
         self.count_local = 0
         self.offset = 0
-        self._flag = None
-        self._outstanding = []
-        self._next_slot = 0
-        # the per-step exchange: peer-memory mailbox over NVLink (hd_mailbox_*) if CUDA IPC works between all ranks,
-        # else an NCCL all-gather of the same 24 bytes
+        self.ctx = C.c_void_p(None)
+        self._check(self._lib.hd_mgpu_create(self.scheme, rank, world, C.byref(p), C.byref(self.ctx)), "hd_mgpu_create")
         self.mailbox = None
-        self.seq = 0
-        if dist is not None and world > 1 and use_mailbox:
-            self._setup_mailbox()
+        self._cb = None
+        if world > 1:
+            if allgather is not None:      # caller-supplied exchange: allgather(d_send, d_recv, nbytes, stream, user) -> 0
+                self._cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p)(allgather)
+                self._check(self._lib.hd_mgpu_exchange_callback(self.ctx, self._cb, None), "hd_mgpu_exchange_callback")
+                return
+            if dist is not None and use_mailbox:
+                self._setup_mailbox()
+            if self.mailbox is not None:
+                self._check(self._lib.hd_mgpu_exchange_mailbox(self.ctx, self.mailbox), "hd_mgpu_exchange_mailbox")
+            else:
+                self._setup_callback()
 
     def _setup_mailbox(self):
+        """Peer-memory mailbox over NVLink (hd_mailbox_*): handles are exchanged once with torch.distributed."""
         torch, L = self.torch, self._lib
         h = C.c_void_p(None)
         ok = L.hd_mailbox_create(self.world, self.rank, C.byref(h)) == 0
@@ -136,115 +161,79 @@ class ShardedSelfSyncDecoder:
         elif h:
             L.hd_mailbox_destroy(h)
 
-    def _exchange(self):
-        """All-gather of self.info into self.all_info, on the stream (collective: every rank calls it)."""
-        if self.mailbox is not None:
-            self.seq += 1
-            sp = self._stream_ptr(self.torch)
-            self._check(self._lib.hd_mailbox_publish(self.mailbox, C.c_void_p(self.info.data_ptr()), self.seq, sp),
-                        "hd_mailbox_publish")
-            self._check(self._lib.hd_mailbox_wait(self.mailbox, self.seq, C.c_void_p(self.all_info.data_ptr()), sp),
-                        "hd_mailbox_wait")
-        elif self.dist is not None and self.world > 1:
-            self.dist.all_gather_into_tensor(self.all_info, self.info)
-        else:
-            self.all_info.copy_(self.info)
+    def _setup_callback(self):
+        """Fallback exchange when CUDA IPC is not available: torch.distributed's (NCCL) all-gather of the 24 bytes,
+        handed to the library as the hd_allgather_fn callback; it works in place on the library's device buffers
+        (zero-copy tensor views through __cuda_array_interface__)."""
+        torch, dist, world = self.torch, self.dist, self.world
+        views = {}
+
+        class _Dev:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+        def allgather(d_send, d_recv, nbytes, stream, user):
+            try:
+                key = (d_send, d_recv)
+                if key not in views:
+                    views[key] = (torch.as_tensor(_Dev(d_send, nbytes // 8), device="cuda"),
+                                  torch.as_tensor(_Dev(d_recv, nbytes // 8 * world), device="cuda"))
+                send, recv = views[key]
+                dist.all_gather_into_tensor(recv, send)
+                return 0
+            except Exception:
+                return 1
+        self._cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p)(allgather)
+        self._check(self._lib.hd_mgpu_exchange_callback(self.ctx, self._cb, None), "hd_mgpu_exchange_callback")
+
+    # ---- the step
+    def step(self):
+        """The timed step, entirely on the stream (hd_mgpu_enqueue): local shard decode + the exchange of {count,
+        entry, exit}.  Several steps may be enqueued back to back; call wait() / finish() before using the results."""
+        self._check(self._lib.hd_mgpu_enqueue(self.ctx, self._stream_ptr(self.torch)), "hd_mgpu_enqueue")
 
     def align(self):
-        """Stream-side rendezvous of the ranks (one exchange round whose result nobody reads): used by bench.py after
-        the untimed L2 flush, so that a rank whose flush ran longer is not waited for inside the next timed step."""
+        """Stream-side rendezvous of the ranks (hd_mgpu_align: one exchange round whose result nobody reads): used by
+        bench.py after the untimed L2 flush, so that a rank whose flush ran longer is not waited for inside the next
+        timed step."""
         if self.world > 1:
-            self._exchange()
-
-    def close(self):
-        if self.mailbox is not None:
-            self.torch.cuda.synchronize()
-            if self.dist is not None:
-                self.dist.barrier()          # nobody may still be writing into a mailbox that is about to go
-            self._lib.hd_mailbox_destroy(self.mailbox)
-            self.mailbox = None
-
-    def _args(self, first_bit, halo):
-        hu = self.n_units_halo if halo else 0
-        ptr = self.d_units.data_ptr() + 4 * (self.n_units_halo - hu)
-        return (C.c_void_p(ptr), hu, self.n_units_local, self.n_units_readable - (self.n_units_halo - hu), first_bit,
-                self.table.handle, C.c_void_p(self.out.data_ptr()), self.out_cap, C.c_void_p(self.ws_ptr), self.ws_bytes,
-                C.c_void_p(self.info.data_ptr()))
-
-    def _decode(self, first_bit=0, halo=True):
-        """Synchronous shard decode (hd_decode_selfsync_shard)."""
-        self._check(self._lib.hd_decode_selfsync_shard(*self._args(first_bit, halo), self._stream_ptr(self.torch)),
-                    "hd_decode_selfsync_shard")
-
-    def step(self):
-        """The timed step, entirely on the stream: local shard decode (hd_decode_selfsync_shard_enqueue) + the
-        exchange of {count, entry, exit}.  Several steps may be enqueued back to back (each has its own convergence
-        flag, up to 256 outstanding); call wait() before using the results."""
-        if self._flag is None:
-            self._flag = self.torch.zeros(256, dtype=self.torch.int32).pin_memory()
-        if len(self._outstanding) >= 256:
-            self.wait()
-        slot = self._next_slot
-        self._next_slot = (slot + 1) % 256
-        self._outstanding.append(slot)
-        args = self._args(0, True) + (C.c_void_p(self._flag.data_ptr() + 4 * slot), self._stream_ptr(self.torch))
-        self._check(self._lib.hd_decode_selfsync_shard_enqueue(*args), "hd_decode_selfsync_shard_enqueue")
-        self._exchange()
-
-    def wait(self):
-        """Host half of the enqueued steps: synchronise the stream and look at their convergence flags.  In the rare
-        unconverged case (a parse that did not synchronise within 64 Kbit) the shard is decoded again synchronously
-        (iterating the synchronisation to its fixed point) and the counts are exchanged again."""
-        if not self._outstanding:
-            return
-        self.torch.cuda.current_stream().synchronize()
-        redone = 0
-        for slot in self._outstanding:
-            if int(self._flag[slot].item()):
-                redone = 1
-        self._outstanding = []
-        if redone:
-            self._decode()
-        # every rank must take part in a re-exchange if ANY rank had to decode again
-        if self.dist is not None and self.world > 1:
-            t = self.torch.tensor([redone], dtype=self.torch.int64, device="cuda")
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-            if int(t.item()):
-                self._exchange()
-                self.torch.cuda.current_stream().synchronize()
-        elif redone:
-            self.all_info.copy_(self.info)
-        if self.mailbox is not None and self._lib.hd_mailbox_timed_out(self.mailbox):
-            raise RuntimeError("shard exchange timed out: a peer rank never published its counts")
-
-    def _gather(self):
-        self._exchange()
-        return self.all_info.cpu().numpy().reshape(self.world, 3)
+            self._check(self._lib.hd_mgpu_align(self.ctx, self._stream_ptr(self.torch)), "hd_mgpu_align")
 
     def finish(self):
-        """Host side of the exchange: check the seams, repair if a halo was too short, place the outputs."""
-        self.wait()
-        infos = self.all_info.cpu().numpy().reshape(self.world, 3)
-        placed = resolve_seams(self.rank, self.world, infos, self._gather,
-                               lambda first_bit: self._decode(first_bit=first_bit, halo=False), self.n_symbols)
-        self.offset, self.count_local = placed[self.rank]
-        return placed
+        """Collective host half (hd_mgpu_finish): convergence, seams, repair, output placement of this rank."""
+        off, cnt = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._lib.hd_mgpu_finish(self.ctx, self.n_symbols, C.byref(off), C.byref(cnt),
+                                             self._stream_ptr(self.torch)), "hd_mgpu_finish")
+        self.offset, self.count_local = int(off.value), int(cnt.value)
+        return self.placed()
+
+    wait = finish
+
+    def infos(self):
+        a = np.zeros((self.world, 3), dtype=np.uint64)
+        self._check(self._lib.hd_mgpu_infos(self.ctx, a.ctypes.data), "hd_mgpu_infos")
+        return a
+
+    def repairs(self):
+        """decodes this rank repeated in the last finish() (hd_mgpu_repair_count)"""
+        return int(self._lib.hd_mgpu_repair_count(self.ctx))
+
+    def placed(self):
+        return place_outputs([int(c) for c in self.infos()[:, 0]], self.n_symbols)
 
     def verify(self, data):
         self.step()
-        self.finish()
+        placed = self.finish()
         want = self.torch.from_numpy(np.ascontiguousarray(data[self.offset:self.offset + self.count_local])).cuda()
-        total = sum(c for _, c in place_outputs(self.all_info.cpu().numpy().reshape(self.world, 3)[:, 0],
-                                                self.n_symbols))
+        total = sum(c for _, c in placed)
         return total == self.n_symbols and bool(self.torch.equal(self.out[:self.count_local], want))
 
     def gather_output(self, dst=0):
         """Optional last step: collect the sharded output on rank `dst` over NVLink.  finish() must have
-        placed the outputs (every rank knows all counts and offsets).  Point-to-point NCCL sends of each rank's bytes
-        straight into their place in the destination buffer; returns the whole output on `dst`, None elsewhere."""
+        placed the outputs.  Point-to-point NCCL sends of each rank's bytes straight into their place in the
+        destination buffer; returns the whole output on `dst`, None elsewhere."""
         torch, dist = self.torch, self.dist
-        infos = self.all_info.cpu().numpy().reshape(self.world, 3)
-        placed = place_outputs(infos[:, 0], self.n_symbols)
+        placed = self.placed()
         if self.world == 1 or dist is None:
             return self.out[:self.count_local]
         if self.rank == dst:
@@ -259,36 +248,105 @@ class ShardedSelfSyncDecoder:
             dist.send(self.out[:self.count_local], dst=dst)
         return None
 
+    def close(self):
+        if self.ctx:
+            self.torch.cuda.synchronize()
+            if self.dist is not None and self.world > 1:
+                self.dist.barrier()          # nobody may still be writing into a mailbox that is about to go
+            self._lib.hd_mgpu_destroy(self.ctx)
+            self.ctx = C.c_void_p(None)
+            if self.mailbox is not None:
+                self._lib.hd_mailbox_destroy(self.mailbox)
+                self.mailbox = None
+
+    # ---- end to end from / to pinned host memory
+    def _upload(self):
+        raise NotImplementedError
+
     def e2e(self, data, steps=5):
-        """Host-buffer path: pinned shard -> H2D -> decode + all-gather -> D2H, wall clock, max over ranks."""
+        """Host-buffer path: pinned shard -> H2D -> decode + exchange -> D2H, wall clock, max over ranks."""
         import time
         torch = self.torch
-        h_in = torch.from_numpy(self.h_units.view(np.int32)).pin_memory()
-        h_out = torch.empty(self.count_local, dtype=torch.uint8).pin_memory()
+        self.finish()
+        h_out = torch.empty(max(1, self.count_local), dtype=torch.uint8).pin_memory()
         tot = 0.0
         for i in range(steps + 1):
-            if self.dist is not None:
+            if self.dist is not None and self.world > 1:
                 self.dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            self.d_units.copy_(h_in, non_blocking=True)
+            self._upload()
             self.step()
-            self.wait()
-            h_out.copy_(self.out[:self.count_local], non_blocking=True)
+            self.finish()
+            h_out[:self.count_local].copy_(self.out[:self.count_local], non_blocking=True)
             torch.cuda.synchronize()
             if i:
                 tot += time.perf_counter() - t0
         t = torch.tensor([tot / steps], dtype=torch.float64, device="cuda")
-        if self.dist is not None:
+        if self.dist is not None and self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        ok = bool(np.array_equal(h_out.numpy(), data[self.offset:self.offset + self.count_local]))
+        ok = bool(np.array_equal(h_out.numpy()[:self.count_local], data[self.offset:self.offset + self.count_local]))
         if not ok:
             raise RuntimeError("host-buffer shard decode mismatch")
-        h2d = torch.tensor([h_in.numel() * 4], dtype=torch.int64, device="cuda")
-        d2h = torch.tensor([h_out.numel()], dtype=torch.int64, device="cuda")
-        if self.dist is not None:
+        h2d = torch.tensor([self._h2d_bytes()], dtype=torch.int64, device="cuda")
+        d2h = torch.tensor([self.count_local], dtype=torch.int64, device="cuda")
+        if self.dist is not None and self.world > 1:
             self.dist.all_reduce(h2d)
             self.dist.all_reduce(d2h)
         return {"value": round(self.n_symbols / float(t.item()) / 1e9, 3), "unit": "GB/s",
                 "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item()), "steps": steps,
-                "api": "ShardedSelfSyncDecoder (pinned host shard in/out, wall clock, max over ranks)"}
+                "api": "%s (pinned host shard in/out, wall clock, max over ranks)" % type(self).__name__}
+
+
+class ShardedSelfSyncDecoder(_ShardedDecoder):
+    """One rank's shard of a self-synchronising decode (CUDA, hd_mgpu_* with HD_SCHEME_SELFSYNC)."""
+    scheme = SCHEME_SELFSYNC
+
+    def __init__(self, units, table, n_symbols, rank, world, dist=None, halo_segments=HALO_SEGMENTS, use_mailbox=True,
+                 allgather=None):
+        self._setup(len(units), table, n_symbols, rank, world, dist, use_mailbox, halo_segments, allgather)
+        torch, p = self.torch, self.plan
+        u0, n = int(p.first_unit), max(4, int(p.readable_units))
+        self.h_units = np.zeros(n, dtype=np.uint32)
+        self.h_units[:int(p.readable_units)] = units[u0:u0 + int(p.readable_units)]   # private copy of the shard
+        self.h_in = torch.from_numpy(self.h_units.view(np.int32)).pin_memory()
+        self.d_units = self.h_in.cuda()
+        self._check(self._lib.hd_mgpu_bind(self.ctx, C.c_void_p(self.d_units.data_ptr()), None, table.handle,
+                                           C.c_void_p(self.out.data_ptr()), C.c_void_p(self.ws_ptr)), "hd_mgpu_bind")
+
+    def _upload(self):
+        self.d_units.copy_(self.h_in, non_blocking=True)
+
+    def _h2d_bytes(self):
+        return self.h_in.numel() * 4
+
+
+class ShardedGapDecoder(_ShardedDecoder):
+    """One rank's shard of a gap-array decode (hd_mgpu_* with HD_SCHEME_GAP): the segment entry rule of
+    decoder.cu:505-507 makes every 128-bit segment boundary a valid entry point, so shards need no halo and no repair;
+    only the symbol counts are exchanged to place the outputs."""
+    scheme = SCHEME_GAP
+
+    def __init__(self, units, gap_words, table, n_symbols, rank, world, dist=None, use_mailbox=True, allgather=None):
+        self._setup(len(units), table, n_symbols, rank, world, dist, use_mailbox, 0, allgather)
+        torch, p = self.torch, self.plan
+        u0, n = int(p.first_unit), max(4, int(p.readable_units))
+        self.h_units = np.zeros(n, dtype=np.uint32)
+        self.h_units[:int(p.readable_units)] = units[u0:u0 + int(p.readable_units)]
+        g0, ng = int(p.first_gap_word), max(1, int(p.n_gap_words))
+        self.h_gaps = np.zeros(ng, dtype=np.uint32)
+        self.h_gaps[:int(p.n_gap_words)] = gap_words[g0:g0 + int(p.n_gap_words)]
+        self.h_in = torch.from_numpy(self.h_units.view(np.int32)).pin_memory()
+        self.h_gin = torch.from_numpy(self.h_gaps.view(np.int32)).pin_memory()
+        self.d_units = self.h_in.cuda()
+        self.d_gaps = self.h_gin.cuda()
+        self._check(self._lib.hd_mgpu_bind(self.ctx, C.c_void_p(self.d_units.data_ptr()), C.c_void_p(self.d_gaps.data_ptr()),
+                                           table.handle, C.c_void_p(self.out.data_ptr()), C.c_void_p(self.ws_ptr)),
+                    "hd_mgpu_bind")
+
+    def _upload(self):
+        self.d_units.copy_(self.h_in, non_blocking=True)
+        self.d_gaps.copy_(self.h_gin, non_blocking=True)
+
+    def _h2d_bytes(self):
+        return (self.h_in.numel() + self.h_gin.numel()) * 4

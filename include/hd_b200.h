@@ -76,7 +76,7 @@ hd_status hd_table_from_lengths(const hd_sym_len *pairs, uint32_t n_pairs,
                                 void *stream, hd_table **out);
 /* Same tables built ON THE DEVICE by a kernel from a device-resident list
  * (e.g. the header of a .huff image that is already in HBM): no host-side
- * table construction and no table upload; only a 16-byte summary is read back.
+ * table construction and no table upload; only a 20-byte summary is read back.
  * Replaces get_table_info/get_twolevel_table (decoder/src/get_table.cpp:3-139)
  * and get_decoder_table (llhuffman_encoder.cc:240-262).  Synchronises `stream`. */
 hd_status hd_table_from_lengths_device(const hd_sym_len *d_pairs, uint32_t n_pairs,
@@ -94,7 +94,8 @@ uint32_t hd_table_min_length(const hd_table *t);
  * per-segment output_pos array of decoder.cu:754.  Ours: one 64-bit status word,
  * padded to a 32-byte sector, per 256 segments (an upper bound: the kernel's
  * tiles hold 512-1728 segments) + (self-sync) 4 bits per 128-bit subsequence,
- * one byte per 16 subsequences and one word per 496. */
+ * one byte per 16 subsequences and one word per 496 -- about 0.035 B per
+ * stream byte. */
 size_t hd_workspace_bytes_gap(uint64_t n_units);
 size_t hd_workspace_bytes_selfsync(uint64_t n_units);
 
@@ -384,6 +385,89 @@ hd_status hd_mailbox_wait(hd_mailbox *m, uint64_t seq, uint64_t *d_all_info3,
                           void *stream);
 int hd_mailbox_timed_out(hd_mailbox *m);
 void hd_mailbox_destroy(hd_mailbox *m);
+
+/* One shard of a gap-array stream: like hd_decode_gap_ex, for a rank that holds
+ * only its part of the stream.  n_units_readable counts the units from the
+ * shard's first segment on that may be read (shard + right halo), n_segments
+ * the segments to decode.  entry_from_prev_word != 0: the shard does not start
+ * the stream; d_gap_words[-1] must be readable and its top nibble is the offset
+ * at which the shard's first segment starts (decoder.cu:505-507).
+ * d_shard_info receives {symbols written, entry offset, exit offset}. */
+hd_status hd_decode_gap_shard(const uint32_t *d_units, uint64_t n_units_readable,
+                              const uint32_t *d_gap_words, uint64_t n_segments,
+                              int entry_from_prev_word, const hd_table *table,
+                              uint8_t *d_out, uint64_t out_cap, void *d_workspace,
+                              size_t workspace_bytes, uint64_t *d_shard_info,
+                              void *stream);
+
+/* hd_mgpu_*: the whole sharded decode of ONE stream over the GPUs of a box,
+ * both schemes (replaces gpuhd/multigpu_demo.cc:178-313: partition :178-227,
+ * per-GPU launch :255-298, host stitch :301-313).  One hd_mgpu per rank (one
+ * process per GPU, or one host thread per GPU).  Life cycle:
+ *   hd_mgpu_plan_shard   pure host arithmetic: which units / gap words this rank
+ *                        uploads, buffer sizes
+ *   hd_mgpu_create + one of hd_mgpu_exchange_{mailbox,nccl,callback}
+ *   hd_mgpu_bind         device buffers of the rank (filled by the caller as the
+ *                        plan says: d_units from plan.first_unit on,
+ *                        d_gap_words from plan.first_gap_word on)
+ *   hd_mgpu_enqueue      shard decode + exchange of {count, entry, exit} on the
+ *                        stream, no host synchronisation (may be repeated)
+ *   hd_mgpu_finish       COLLECTIVE host half: reads the exchanged triples,
+ *                        repeats decodes whose synchronisation had not
+ *                        converged, repairs seams (entry[g] != exit[g-1]: rank g
+ *                        decodes again from the exact offset, a sequential
+ *                        chain in the never-synchronising worst case), then
+ *                        returns this rank's output placement: its bytes
+ *                        d_out[0, count) belong at `offset` of the whole output.
+ * No payload crosses NVLink; the output stays sharded. */
+typedef enum { HD_SCHEME_SELFSYNC = 0, HD_SCHEME_GAP = 1 } hd_scheme;
+typedef struct {
+    uint64_t seg_begin, seg_end;   /* 128-bit segments [begin, end) of the stream decoded by this rank */
+    uint64_t first_unit;           /* first unit of the stream the rank uploads */
+    uint64_t halo_units;           /* self-sync: units before the shard, parsed speculatively */
+    uint64_t shard_units;          /* units of the shard proper; 0 = nothing to decode (more ranks than tiles) */
+    uint64_t readable_units;       /* units to upload from first_unit on: halo + shard + right halo */
+    uint64_t first_gap_word;       /* gap scheme: first gap word the rank uploads ... */
+    uint64_t n_gap_words;          /* ... and how many */
+    uint64_t out_capacity;         /* bytes of the rank's output buffer (worst case of the code's shortest length) */
+    uint64_t workspace_bytes;
+} hd_mgpu_plan;
+/* halo_segments: 0 = default (4096 segments = 64 KiB of stream) */
+hd_status hd_mgpu_plan_shard(hd_scheme scheme, uint64_t n_units, uint32_t rank,
+                             uint32_t world, uint32_t min_code_length,
+                             uint64_t halo_segments, hd_mgpu_plan *plan);
+/* pure host: the seam rule and the output placement over gathered triples
+ * (world x {count, entry, exit}); first_bad_seam returns world if all agree */
+uint32_t hd_mgpu_first_bad_seam(const uint64_t *infos, uint32_t world);
+void hd_mgpu_place(const uint64_t *infos, uint32_t world, uint64_t n_symbols,
+                   uint32_t rank, uint64_t *offset, uint64_t *count);
+
+typedef struct hd_mgpu hd_mgpu;
+/* all-gather of bytes_per_rank bytes per rank on `stream`; 0 = success */
+typedef int (*hd_allgather_fn)(const void *d_send, void *d_recv,
+                               size_t bytes_per_rank, void *stream, void *user);
+hd_status hd_mgpu_create(hd_scheme scheme, uint32_t rank, uint32_t world,
+                         const hd_mgpu_plan *plan, hd_mgpu **out);
+void hd_mgpu_destroy(hd_mgpu *m);
+/* the exchange: a connected mailbox handle -- peer memory over NVLink --, the rank's
+ * ncclComm_t (passed as void*; ncclAllGather of the NCCL already loaded in the
+ * process -- the library does not link against NCCL), or any callback */
+hd_status hd_mgpu_exchange_mailbox(hd_mgpu *m, hd_mailbox *mailbox);
+hd_status hd_mgpu_exchange_nccl(hd_mgpu *m, void *nccl_comm);
+hd_status hd_mgpu_exchange_callback(hd_mgpu *m, hd_allgather_fn fn, void *user);
+hd_status hd_mgpu_bind(hd_mgpu *m, const uint32_t *d_units,
+                       const uint32_t *d_gap_words /* NULL for self-sync */,
+                       const hd_table *table, uint8_t *d_out, void *d_workspace);
+hd_status hd_mgpu_enqueue(hd_mgpu *m, void *stream);
+/* one exchange round whose result nobody reads (benchmarks: rendezvous of the
+ * ranks on the stream) */
+hd_status hd_mgpu_align(hd_mgpu *m, void *stream);
+hd_status hd_mgpu_finish(hd_mgpu *m, uint64_t n_symbols_total, uint64_t *offset,
+                         uint64_t *count, void *stream);
+/* the triples of the last hd_mgpu_finish (world x 3, host), and how many times
+ * THIS rank had to decode again in it (0 in the normal case) */
+hd_status hd_mgpu_infos(const hd_mgpu *m, uint64_t *infos_out);
+uint32_t hd_mgpu_repair_count(const hd_mgpu *m);
 
 #ifdef __cplusplus
 }

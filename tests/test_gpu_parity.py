@@ -309,46 +309,89 @@ def test_1GiB_gap_roundtrip(hd, torch_cuda):
     assert same and cnt == n
 
 
-# ---------------------------------------------------------------- multi-GPU shard entry (ranks emulated on one device)
-def _sharded_selfsync(hd, units, lut, n, world, halo_segments):
+# ---------------------------------------------------------------- multi-GPU layer (hd_mgpu_*), ranks emulated on one device
+class _ThreadGather:
+    """A real collective between `world` host threads of this process (one thread per emulated rank, all on cuda:0):
+    the hd_allgather_fn callback handed to hd_mgpu_exchange_callback."""
+
+    def __init__(self, world, torch):
+        import threading
+        self.world, self.torch = world, torch
+        self.barrier = threading.Barrier(world)
+        self.table = np.zeros((world, 3), dtype=np.uint64)
+
+    def callback(self, rank):
+        torch, world = self.torch, self.world
+
+        class Dev:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+        def allgather(d_send, d_recv, nbytes, stream, user):
+            try:
+                torch.cuda.synchronize()
+                send = torch.as_tensor(Dev(d_send, 3), device="cuda")
+                self.table[rank] = send.cpu().numpy().view(np.uint64)
+                self.barrier.wait(timeout=120)
+                recv = torch.as_tensor(Dev(d_recv, 3 * world), device="cuda")
+                recv.copy_(torch.from_numpy(self.table.reshape(-1).view(np.int64).copy()))
+                torch.cuda.synchronize()
+                self.barrier.wait(timeout=120)
+                return 0
+            except Exception:
+                return 1
+        return allgather
+
+
+def _run_ranks(torch, world, make):
+    """make(rank, allgather) -> a sharded decoder; every emulated rank runs step() + finish() on its own host thread.
+    Returns (whole output, first-round infos of rank 0, placement, repairs per rank)."""
+    import threading
+    tg = _ThreadGather(world, torch)
+    res, err = [None] * world, []
+
+    def run(rank):
+        try:
+            torch.cuda.set_device(0)
+            d = make(rank, tg.callback(rank) if world > 1 else None)
+            d.step()
+            placed = d.finish()
+            res[rank] = (d.out[:d.count_local].cpu().numpy(), d.infos().copy(), placed, d.repairs(), d.offset)
+            tg.barrier.wait(timeout=120) if world > 1 else None
+            d.dist = None
+            d.close()
+        except Exception as e:   # noqa: BLE001
+            err.append(e)
+            tg.barrier.abort()
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if err:
+        raise err[0]
+    for r in range(1, world):
+        assert np.array_equal(res[r][1], res[0][1]) and res[r][2] == res[0][2]     # every rank holds the same triples
+    return np.concatenate([x[0] for x in res]), res[0][1], res[0][2], [x[3] for x in res]
+
+
+def _sharded_selfsync(hd, torch, units, lut, n, world, halo_segments):
     tab = hd.Codetable(flat_lut=lut)
-    decs = [hd.ShardedSelfSyncDecoder(units, tab, n, g, world, dist=None, halo_segments=halo_segments)
-            for g in range(world)]
-    for d in decs:
-        d._decode()
-    infos = [d.info.cpu().numpy().copy() for d in decs]
-
-    def gather():
-        return np.stack([d.info.cpu().numpy() for d in decs])
-
-    # all emulated ranks step the seam protocol of sharding.resolve_seams in lockstep: the first wrong seam is
-    # repaired by its own rank from the predecessor's exact exit offset, then everybody re-gathers
-    redone = []
-    for _ in range(world):
-        cur = gather()
-        bad = hd.seams_ok(cur)
-        if not bad:
-            break
-        g = bad[0]
-        decs[g]._decode(first_bit=int(cur[g - 1][2]), halo=False)
-        redone.append(g)
-    else:
-        raise AssertionError("seams did not converge")
-    placed = hd.place_outputs([row[0] for row in gather()], n)
-    parts = [d.out[:placed[g][1]].cpu().numpy() for g, d in enumerate(decs)]
+    out = _run_ranks(torch, world, lambda r, ag: hd.ShardedSelfSyncDecoder(units, tab, n, r, world, dist=None,
+                                                                           halo_segments=halo_segments, allgather=ag))
     tab.close()
-    return np.concatenate(parts), infos, placed, redone
+    return out
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_selfsync_shards_with_halo(hd, torch_cuda, world):
     n = 5_000_000
     data = O.generate(n, 0.5, seed=41)
     pairs = hd.build_code(data, 11)
     lut = hd.flat_lut(pairs, 11)
     units, bits = hd.encode(data, pairs, pad_unit=True)
-    whole, infos, placed, redone = _sharded_selfsync(hd, units, lut, n, world, 4096)
-    assert redone == []                                  # the halo synchronised every seam
+    whole, infos, placed, repairs = _sharded_selfsync(hd, torch_cuda, units, lut, n, world, 4096)
+    assert repairs == [0] * world                        # the halo synchronised every seam
     assert hd.seams_ok(infos) == []
     assert sum(c for _, c in placed) == n
     assert np.array_equal(whole, data)
@@ -359,26 +402,60 @@ def test_selfsync_shards_with_halo(hd, torch_cuda, world):
     codes, lens = O.canonical_codes(pairs[:, 0], pairs[:, 1])
     for g in range(1, world):
         seg = plan[g][0]
-        assert int(off[seg]) <= int(infos[g][1]) <= 15
+        entry = int(infos[g][1]) & 0xffff
+        assert int(off[seg]) <= entry <= 15
         # walk the true parse from the segment's first codeword: the entry must be one of its boundaries
         k = int(cnt[:seg].sum())
         pos = int(off[seg])
-        while pos < int(infos[g][1]):
+        while pos < entry:
             pos += int(lens[data[k]])
             k += 1
-        assert pos == int(infos[g][1])
+        assert pos == entry
 
 
 def test_selfsync_shards_repair_when_code_never_synchronises(hd, torch_cuda):
-    """All-3-bit code: the halo cannot synchronise, the seam check catches it and the shard is re-decoded from the
-    predecessor's exact exit offset (sequential chain across ranks)."""
+    """All-3-bit code: the halo cannot synchronise, hd_mgpu_finish catches it at the seams and the shards are decoded
+    again from their predecessors' exact exit offsets (sequential chain across ranks)."""
     pairs = cases.fixed_length_code(8, 3)
     n = 2_000_003
     data = cases.data_for_pairs(pairs, n, seed=6)
     units, gw, bits, lut = cases.oracle_stream(data, pairs, pad_unit=True)
-    whole, infos, placed, redone = _sharded_selfsync(hd, units, lut, n, 4, 1024)
+    whole, infos, placed, repairs = _sharded_selfsync(hd, torch_cuda, units, lut, n, 4, 1024)
     assert np.array_equal(whole, data)
     assert sum(c for _, c in placed) == n
+    assert sum(repairs[1:]) >= 3                       # every later shard had to be decoded again at least once
+
+
+def test_selfsync_shards_more_ranks_than_tiles(hd, torch_cuda):
+    """fewer 256-segment tiles than ranks -> ranks without segments publish an empty triple instead of
+    failing (which used to leave the other ranks waiting in the exchange)."""
+    n = 9000                                           # ~1670 units = 2 tiles
+    data = O.generate(n, 0.5, seed=43)
+    pairs = hd.build_code(data, 11)
+    lut = hd.flat_lut(pairs, 11)
+    units, bits = hd.encode(data, pairs, pad_unit=True)
+    whole, infos, placed, repairs = _sharded_selfsync(hd, torch_cuda, units, lut, n, 4, 4096)
+    assert np.array_equal(whole, data) and sum(c for _, c in placed) == n
+    assert sum(1 for row in infos if int(row[1]) == (1 << 64) - 1) >= 2
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("r", [0.5, 0.9])
+def test_gap_shards_through_hd_mgpu(hd, torch_cuda, world, r):
+    """gap-array shards (segment entry rule decoder.cu:505-507) through hd_mgpu_* -- no halo, no
+    repair, only the counts place the outputs.  16-bit limited .huff code."""
+    n = 6_000_011
+    data = O.generate(n, r, seed=int(100 * r) + world)
+    pairs = hd.build_code(data, 16)
+    units, gaps, bits = hd.encode(data, pairs, want_gaps=True)
+    tab = hd.Codetable(pairs=pairs)
+    whole, infos, placed, repairs = _run_ranks(
+        torch_cuda, world, lambda rk, ag: hd.ShardedGapDecoder(units, gaps, tab, n, rk, world, dist=None, allgather=ag))
+    tab.close()
+    assert repairs == [0] * world and hd.seams_ok(infos) == []
+    assert sum(c for _, c in placed) == n and np.array_equal(whole, data)
+    want = O.decode_gap(units, gaps, (len(units) + 3) // 4, O.flat_lut(*O.canonical_codes(pairs[:, 0], pairs[:, 1]), 16), n)
+    assert np.array_equal(whole, want)
 
 
 def test_host_decoder_selfsync_and_huff(hd, torch_cuda):

@@ -32,6 +32,48 @@ def test_plan_covers_stream_on_tile_boundaries(hd):
                 assert (sb, se) == (b, e)
 
 
+def test_plan_shard_fields_both_schemes(hd):
+    """hd_mgpu_plan_shard: units / gap words a rank uploads (pure host arithmetic of the C ABI)."""
+    n_units = 4 * 256 * 9 + 2                      # 10 tiles, the last one partial
+    n_seg = (n_units + 3) // 4
+    for world in (1, 2, 3, 8):
+        covered = 0
+        for r in range(world):
+            g = hd.plan_shard(hd.SCHEME_GAP, n_units, r, world, 3)
+            s = hd.plan_shard(hd.SCHEME_SELFSYNC, n_units, r, world, 3)
+            assert (g.seg_begin, g.seg_end) == (s.seg_begin, s.seg_end) == hd.shard_segments(n_seg, r, world)
+            assert g.halo_units == 0 and g.first_unit == g.seg_begin * 4
+            assert g.shard_units == min(g.seg_end * 4, n_units) - g.seg_begin * 4
+            assert g.first_unit + g.readable_units <= n_units and g.readable_units >= g.shard_units
+            # gap words: the one before the shard (entry offset of its first segment) up to the one holding seg_end-1
+            assert g.first_gap_word == (g.seg_begin // 8 - 1 if g.seg_begin else 0)
+            assert g.first_gap_word + g.n_gap_words == (g.seg_end + 7) // 8
+            assert s.halo_units % 32 == 0 and s.first_unit == g.first_unit - s.halo_units
+            assert (s.halo_units == 0) == (r == 0)
+            assert g.out_capacity >= (g.shard_units * 32 + 2) // 3
+            covered += g.shard_units
+        assert covered == n_units
+
+
+def test_plan_shard_more_ranks_than_tiles(hd):
+    """a stream with fewer 256-segment tiles than ranks leaves ranks without segments; they take part in the
+    exchange with an 'empty' triple and the seam check chains through them."""
+    n_units = 4 * 256 + 8                          # two tiles
+    plans = [hd.plan_shard(hd.SCHEME_SELFSYNC, n_units, r, 4, 1) for r in range(4)]
+    assert sum(int(p.shard_units) for p in plans) == n_units
+    assert sum(1 for p in plans if p.shard_units == 0) == 2
+    E = (1 << 64) - 1
+    infos = [(100, 0, 5), (0, E, E), (40, 5, 0), (0, E, E)]
+    assert hd.seams_ok(infos) == []
+    assert hd.seams_ok([(100, 0, 5), (0, E, E), (40, 6, 0), (0, E, E)]) == [2]
+    assert hd.place_outputs([100, 0, 40, 0], 130) == [(0, 100), (100, 0), (100, 30), (130, 0)]
+
+
+def test_seam_check_ignores_the_unconverged_flag(hd):
+    """bit 32 of the entry word = "decoded before the synchronisation had converged" (hd_mgpu_finish repeats those)."""
+    assert hd.seams_ok([(5, 0, 3), (6, 3 | (1 << 32), 7), (2, 7, 0)]) == []
+
+
 def test_place_outputs_clamps_last_shard(hd):
     assert hd.place_outputs([10, 20, 35], 60) == [(0, 10), (10, 20), (30, 30)]
     assert hd.place_outputs([10, 0, 5], 12) == [(0, 10), (10, 0), (10, 2)]
