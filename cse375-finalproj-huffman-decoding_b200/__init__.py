@@ -56,7 +56,8 @@ ABI_SYMBOLS = [
     "hd_mailbox_destroy", "hd_decode_gap_shard", "hd_mgpu_plan_shard", "hd_mgpu_first_bad_seam", "hd_mgpu_place",
     "hd_mgpu_create", "hd_mgpu_destroy", "hd_mgpu_exchange_mailbox", "hd_mgpu_exchange_nccl",
     "hd_mgpu_exchange_callback", "hd_mgpu_bind", "hd_mgpu_enqueue", "hd_mgpu_align", "hd_mgpu_finish", "hd_mgpu_infos",
-    "hd_mgpu_repair_count",
+    "hd_mgpu_repair_count", "hd_mgpu_host_step", "hd_mgpu_host_refresh", "hd_host_decode_selfsync_shard",
+    "hd_host_decode_gap_shard", "hd_host_decoder_buffers",
 ]
 PROFILE_SLOTS = ("sync_chunks", "sync_seams", "decode_write", "reserved")
 
@@ -157,6 +158,12 @@ def lib():
     L.hd_mgpu_finish.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(u64), vp]
     L.hd_mgpu_infos.argtypes = [vp, vp]
     L.hd_mgpu_repair_count.argtypes = [vp]
+    L.hd_mgpu_host_step.argtypes = [vp, vp, vp, vp, vp, u64, vp]
+    L.hd_mgpu_host_refresh.argtypes = [vp, vp, u64, vp]
+    L.hd_host_decode_selfsync_shard.argtypes = [vp, vp, u64, u64, u64, vp, vp, u64, vp, vp]
+    L.hd_host_decode_gap_shard.argtypes = [vp, vp, u64, vp, u64, u32, vp, vp, u64, vp, vp]
+    L.hd_host_decoder_buffers.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.hd_host_decoder_buffers.restype = None
     L.hd_mgpu_repair_count.restype = u32
     _lib = L
     return L

@@ -1045,31 +1045,34 @@ static HostPlan host_plan(uint64_t n_seg) {
 }
 
 // serial tail of the pipeline (and the whole of it for codes that do not self-synchronise): pieces i0.. one at a time
+// (base = segments of left halo in front of the piece plan: a shard of a longer stream, see host_decode_common)
 static hd_status host_decode_serial(hd_host_decoder *h, const HostPlan &P, int i0, uint64_t offset, uint64_t prev_exit,
                                     uint64_t n_units, const uint8_t *gap_words, const hd_table *tab, uint8_t *out,
-                                    uint64_t n_symbols) {
+                                    uint64_t n_symbols, uint64_t base = 0, uint32_t first_bit0 = 0,
+                                    uint64_t *info_out = nullptr) {
     uint32_t *d_units = reinterpret_cast<uint32_t *>(h->d_units);
     uint32_t *d_gaps = reinterpret_cast<uint32_t *>(h->d_gaps);
     for (int i = i0; i < P.n_pieces && offset < n_symbols; ++i) {
         const uint64_t s0 = P.seg[i], s1 = P.seg[i + 1];
-        const uint64_t shard_units = std::min<uint64_t>(n_units, s1 * 4) - s0 * 4;
-        const uint64_t readable_end = std::min<uint64_t>(n_units, s1 * 4 + 4);
+        const uint64_t b0 = base + s0, b1 = base + s1;   // segments in the buffer
+        const uint64_t shard_units = std::min<uint64_t>(n_units, b1 * 4) - b0 * 4;
+        const uint64_t readable_end = std::min<uint64_t>(n_units, b1 * 4 + 4);
         HD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_piece[i], 0));
         hd_status st;
         if (gap_words) {
-            uint32_t first_bit = 0;
+            uint32_t first_bit = first_bit0;
             if (s0) {
                 const uint64_t j = s0 - 1;
                 uint32_t w;
                 std::memcpy(&w, gap_words + (j >> 3) * 4, 4);
                 first_bit = (w >> (4u * (uint32_t)(j & 7))) & 15u;
             }
-            st = hd_decode_gap_ex(d_units + s0 * 4, readable_end - s0 * 4, d_gaps + s0 / 8, s1 - s0, first_bit, tab,
+            st = hd_decode_gap_ex(d_units + b0 * 4, readable_end - b0 * 4, d_gaps + s0 / 8, s1 - s0, first_bit, tab,
                                   h->d_out + offset, n_symbols - offset, h->d_ws, h->ws_bytes, h->d_info, h->stream);
         } else {
-            const uint64_t halo = std::min<uint64_t>(kHostHaloSegs, s0);
-            st = hd_decode_selfsync_shard(d_units + (s0 - halo) * 4, halo * 4, shard_units,
-                                          readable_end - (s0 - halo) * 4, 0, tab, h->d_out + offset, n_symbols - offset,
+            const uint64_t halo = s0 ? std::min<uint64_t>(kHostHaloSegs, b0) / 8 * 8 : base;
+            st = hd_decode_selfsync_shard(d_units + (b0 - halo) * 4, halo * 4, shard_units,
+                                          readable_end - (b0 - halo) * 4, 0, tab, h->d_out + offset, n_symbols - offset,
                                           h->d_ws, h->ws_bytes, h->d_info, h->stream);
         }
         if (st != HD_OK) return st;
@@ -1078,7 +1081,7 @@ static hd_status host_decode_serial(hd_host_decoder *h, const HostPlan &P, int i
         if (!gap_words && i > 0 && h->h_info[1] != prev_exit) {
             // the halo did not synchronise this piece (a code that does not self-synchronise within 64 KiB): decode
             // it again from the exact offset at which the previous piece's parse left
-            st = hd_decode_selfsync_shard(d_units + s0 * 4, 0, shard_units, readable_end - s0 * 4, (uint32_t)prev_exit, tab,
+            st = hd_decode_selfsync_shard(d_units + b0 * 4, 0, shard_units, readable_end - b0 * 4, (uint32_t)(prev_exit & 15u), tab,
                                           h->d_out + offset, n_symbols - offset, h->d_ws, h->ws_bytes, h->d_info,
                                           h->stream);
             if (st != HD_OK) return st;
@@ -1086,23 +1089,34 @@ static hd_status host_decode_serial(hd_host_decoder *h, const HostPlan &P, int i
             HD_CUDA(cudaStreamSynchronize(h->stream));
         }
         const uint64_t count = h->h_info[0];
+        if (info_out && i == 0) info_out[1] = h->h_info[1] & 0xffffu;
         prev_exit = h->h_info[2];
         HD_CUDA(cudaMemcpyAsync(out + offset, h->d_out + offset, count, cudaMemcpyDeviceToHost, h->s_d2h));
         offset += count;
     }
     HD_CUDA(cudaStreamSynchronize(h->s_d2h));
     HD_CUDA(cudaStreamSynchronize(h->s_h2d));
+    if (info_out) {   // a shard: the caller learns the count
+        info_out[0] = offset;
+        info_out[2] = prev_exit;
+        return HD_OK;
+    }
     return offset < n_symbols ? HD_ERR_FORMAT : HD_OK;   // FORMAT: the stream holds fewer codewords than asked for
 }
 
+// A SHARD of a longer stream (multi-GPU, hd_host_decode_*_shard) is the same pipeline with three differences: the
+// buffer starts with `base` segments of left halo that are uploaded with the first piece and only parsed (self-sync) --
+// the first piece's entry offset is then speculative and reported, not checked; only n_dec_segs segments are decoded;
+// and the number of symbols is an output (info_out = {count, entry offset of the first piece, exit offset}).
 static hd_status host_decode_common(hd_host_decoder *h, const uint32_t *units, uint64_t n_units,
                                     const uint8_t *gap_words, uint64_t n_segments, const hd_table *tab,
-                                    uint8_t *out, uint64_t n_symbols, float timing_ms[3]) {
+                                    uint8_t *out, uint64_t n_symbols, float timing_ms[3], uint64_t base = 0,
+                                    uint64_t n_dec_segs = 0, uint32_t first_bit0 = 0, uint64_t *info_out = nullptr) {
     if (n_units > h->max_units || n_symbols > h->max_symbols) return HD_ERR_INVALID;
     HD_CUDA(cudaSetDevice(h->device));
     uint32_t *d_units = reinterpret_cast<uint32_t *>(h->d_units);
     uint32_t *d_gaps = reinterpret_cast<uint32_t *>(h->d_gaps);
-    const uint64_t n_seg = div_up(n_units, kSegmentUnits);
+    const uint64_t n_seg = n_dec_segs ? n_dec_segs : div_up(n_units, kSegmentUnits);
     const HostPlan P = host_plan(n_seg);
     const auto t0 = std::chrono::steady_clock::now();
 
@@ -1112,8 +1126,8 @@ static hd_status host_decode_common(hd_host_decoder *h, const uint32_t *units, u
         HD_CUDA(cudaMemcpyAsync(d_gaps, gap_words, div_up(n_segments, 8) * 4, cudaMemcpyHostToDevice, h->s_h2d));
     }
     for (int i = 0; i < P.n_pieces; ++i) {
-        const uint64_t u0 = P.seg[i] * 4;
-        const uint64_t u1 = std::min<uint64_t>(n_units, P.seg[i + 1] * 4 + 4);
+        const uint64_t u0 = i ? (base + P.seg[i]) * 4 : 0;   // (the first piece brings the shard's left halo along)
+        const uint64_t u1 = std::min<uint64_t>(n_units, (base + P.seg[i + 1]) * 4 + 4);
         HD_CUDA(cudaMemcpyAsync(d_units + u0, units + u0, (u1 - u0) * 4, cudaMemcpyHostToDevice, h->s_h2d));
         HD_CUDA(cudaEventRecord(h->ev_piece[i], h->s_h2d));
     }
@@ -1121,28 +1135,29 @@ static hd_status host_decode_common(hd_host_decoder *h, const uint32_t *units, u
     // ---- stage 2: decode piece i into d_out at the offset the previous piece left on the device
     auto enqueue_piece = [&](int i) -> hd_status {
         const uint64_t s0 = P.seg[i], s1 = P.seg[i + 1];
-        const uint64_t shard_units = std::min<uint64_t>(n_units, s1 * 4) - s0 * 4;
-        const uint64_t readable_end = std::min<uint64_t>(n_units, s1 * 4 + 4);
+        const uint64_t b0 = base + s0, b1 = base + s1;   // segments in the buffer
+        const uint64_t shard_units = std::min<uint64_t>(n_units, b1 * 4) - b0 * 4;
+        const uint64_t readable_end = std::min<uint64_t>(n_units, b1 * 4 + 4);
         uint64_t *info = h->d_info + 4 * i;
         const uint64_t *off_in = i ? h->d_info + 4 * (i - 1) + 3 : nullptr;
         HD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_piece[i], 0));
         hd_status st;
         if (gap_words) {
-            uint32_t first_bit = 0;
+            uint32_t first_bit = first_bit0;
             if (s0) {
                 const uint64_t j = s0 - 1;
                 uint32_t w;
                 std::memcpy(&w, gap_words + (j >> 3) * 4, 4);
                 first_bit = (w >> (4u * (uint32_t)(j & 7))) & 15u;
             }
-            const uint64_t piece_units = readable_end - s0 * 4;
+            const uint64_t piece_units = readable_end - b0 * 4;
             Workspace w = carve(h->d_ws, piece_units, false);
-            st = run_gap_decode(d_units + s0 * 4, piece_units, d_gaps + s0 / 8, s1 - s0, first_bit, tab, h->d_out,
+            st = run_gap_decode(d_units + b0 * 4, piece_units, d_gaps + s0 / 8, s1 - s0, first_bit, tab, h->d_out,
                                 n_symbols, w, info, h->stream, 0, nullptr, nullptr, false, off_in, info + 3);
             h->h_flags[i] = 0;
         } else {
-            const uint64_t halo = std::min<uint64_t>(kHostHaloSegs, s0);
-            st = shard_enqueue_impl(d_units + (s0 - halo) * 4, halo * 4, shard_units, readable_end - (s0 - halo) * 4, 0,
+            const uint64_t halo = s0 ? std::min<uint64_t>(kHostHaloSegs, b0) / 8 * 8 : base;
+            st = shard_enqueue_impl(d_units + (b0 - halo) * 4, halo * 4, shard_units, readable_end - (b0 - halo) * 4, 0,
                                     tab, h->d_out, n_symbols, h->d_ws, h->ws_bytes, info, h->h_flags + i, h->stream,
                                     off_in, info + 3);
         }
@@ -1164,9 +1179,10 @@ static hd_status host_decode_common(hd_host_decoder *h, const uint32_t *units, u
     for (int i = 0; i < P.n_pieces; ++i) {
         HD_CUDA(cudaEventSynchronize(h->ev_dec[i]));
         const uint64_t *info = h->h_info + 4 * i;
-        if (!gap_words && (h->h_flags[i] != 0 || (i > 0 && info[1] != prev_exit))) {
+        if (!gap_words && (h->h_flags[i] != 0 || (i > 0 && (info[1] & 0xffffu) != (prev_exit & 0xffffu)))) {
             HD_CUDA(cudaStreamSynchronize(h->stream));   // pieces enqueued ahead decoded to a wrong position: drop them
-            const hd_status st = host_decode_serial(h, P, i, offset, prev_exit, n_units, gap_words, tab, out, n_symbols);
+            const hd_status st = host_decode_serial(h, P, i, offset, prev_exit, n_units, gap_words, tab, out, n_symbols,
+                                                    base, first_bit0, info_out);
             if (timing_ms) {
                 timing_ms[0] = (float)std::chrono::duration<double, std::milli>(t1 - t0).count();
                 timing_ms[1] = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
@@ -1175,6 +1191,7 @@ static hd_status host_decode_common(hd_host_decoder *h, const uint32_t *units, u
             return st;
         }
         const uint64_t count = info[0];
+        if (info_out && i == 0) info_out[1] = info[1] & 0xffffu;
         prev_exit = info[2];
         if (count) HD_CUDA(cudaMemcpyAsync(out + offset, h->d_out + offset, count, cudaMemcpyDeviceToHost, h->s_d2h));
         offset += count;
@@ -1186,7 +1203,12 @@ static hd_status host_decode_common(hd_host_decoder *h, const uint32_t *units, u
     const auto t2 = std::chrono::steady_clock::now();
     HD_CUDA(cudaStreamSynchronize(h->s_d2h));
     HD_CUDA(cudaStreamSynchronize(h->s_h2d));
-    if (offset < n_symbols) return HD_ERR_FORMAT;   // the stream holds fewer codewords than asked for
+    if (info_out) {   // a shard: the caller learns the count
+        info_out[0] = offset;
+        info_out[2] = prev_exit;
+    } else if (offset < n_symbols) {
+        return HD_ERR_FORMAT;   // the stream holds fewer codewords than asked for
+    }
     if (timing_ms) {
         timing_ms[0] = (float)std::chrono::duration<double, std::milli>(t1 - t0).count();
         timing_ms[1] = (float)std::chrono::duration<double, std::milli>(t2 - t1).count();
@@ -1239,6 +1261,42 @@ hd_status hd_host_decode_huff(hd_host_decoder *h, const void *file, size_t size,
     // the payload may be only 2-byte aligned in the file image; cudaMemcpy does not care
     return host_decode_common(h, reinterpret_cast<const uint32_t *>(v.units), v.n_units, v.gap_words, v.n_segments,
                               h->cached_table, out, v.original_size, timing_ms);
+}
+
+// One rank's shard of a longer stream from / to HOST buffers (multi-GPU end to end: every rank runs the same
+// three-stage pipeline over its shard; hd_mgpu_host_step adds the exchange of the counts).  units -> [left halo | shard
+// | right halo] as hd_mgpu_plan_shard lays it out; info_out = {symbols written to out, entry offset, exit offset}.
+hd_status hd_host_decode_selfsync_shard(hd_host_decoder *h, const uint32_t *units, uint64_t n_units_halo,
+                                        uint64_t n_units_shard, uint64_t n_units_readable, const hd_table *table,
+                                        uint8_t *out, uint64_t out_cap, uint64_t info_out[3], float timing_ms[3]) {
+    if (!h || !units || !table || !out || !info_out || n_units_shard == 0) return HD_ERR_INVALID;
+    if (n_units_halo % (kSegmentUnits * 8) || n_units_readable < n_units_halo + n_units_shard) return HD_ERR_INVALID;
+    return host_decode_common(h, units, n_units_readable, nullptr, 0, table, out, std::min<uint64_t>(out_cap, h->max_symbols),
+                              timing_ms, n_units_halo / kSegmentUnits, div_up(n_units_shard, kSegmentUnits), 0, info_out);
+}
+
+// gap_words: the shard's own elements (element 0 = entry offset of the shard's segment 1); entry_bit = offset at
+// which the shard's first segment starts (decoder.cu:505-507: the gap element before the shard)
+hd_status hd_host_decode_gap_shard(hd_host_decoder *h, const uint32_t *units, uint64_t n_units_readable,
+                                   const uint32_t *gap_words, uint64_t n_segments, uint32_t entry_bit,
+                                   const hd_table *table, uint8_t *out, uint64_t out_cap, uint64_t info_out[3],
+                                   float timing_ms[3]) {
+    if (!h || !units || !gap_words || !table || !out || !info_out || n_segments == 0 || entry_bit > 15) return HD_ERR_INVALID;
+    if (n_segments > div_up(n_units_readable, kSegmentUnits)) return HD_ERR_INVALID;
+    return host_decode_common(h, units, n_units_readable, reinterpret_cast<const uint8_t *>(gap_words), n_segments, table, out,
+                              std::min<uint64_t>(out_cap, h->max_symbols), timing_ms, 0, n_segments, entry_bit, info_out);
+}
+
+// device buffers of a host decoder (after a call they hold the uploaded units and the decoded output): lets the
+// multi-GPU layer repeat a shard decode on the device in the rare repair case
+void hd_host_decoder_buffers(hd_host_decoder *h, uint32_t **d_units, uint32_t **d_gap_words, uint8_t **d_out,
+                             void **d_workspace, size_t *workspace_bytes) {
+    if (!h) return;
+    if (d_units) *d_units = reinterpret_cast<uint32_t *>(h->d_units);
+    if (d_gap_words) *d_gap_words = reinterpret_cast<uint32_t *>(h->d_gaps);
+    if (d_out) *d_out = h->d_out;
+    if (d_workspace) *d_workspace = h->d_ws;
+    if (workspace_bytes) *workspace_bytes = h->ws_bytes;
 }
 
 // One-shot `./bin/demo` shape (gpuhd/src/demo.cc:155-197): allocate, H2D, decode, D2H, free.

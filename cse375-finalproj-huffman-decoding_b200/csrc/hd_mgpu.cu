@@ -68,6 +68,7 @@ struct hd_mgpu {
     uint64_t *d_info = nullptr;     // {count, entry | unconverged << 32, exit}
     uint64_t *d_all = nullptr;      // world x 3
     uint32_t *h_flags = nullptr;    // pinned ring of convergence flags (one per enqueued step)
+    uint64_t *h_info = nullptr;     // pinned: the triple of a host-buffer step (hd_mgpu_host_step)
     int next_flag = 0;
     bool pending = false;
     uint32_t repairs = 0;           // decodes repeated by the last hd_mgpu_finish (unconverged + seam repairs)
@@ -155,6 +156,7 @@ hd_status hd_mgpu_create(hd_scheme scheme, uint32_t rank, uint32_t world, const 
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&m->d_info), 3 * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&m->d_all), 3 * sizeof(uint64_t) * world);
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&m->h_flags), kFlagRing * sizeof(uint32_t), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&m->h_info), 4 * sizeof(uint64_t), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMemset(m->d_info, 0, 3 * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMemset(m->d_all, 0, 3 * sizeof(uint64_t) * world);
     if (e != cudaSuccess) {
@@ -172,6 +174,7 @@ void hd_mgpu_destroy(hd_mgpu *m) {
     if (m->d_info) cudaFree(m->d_info);
     if (m->d_all) cudaFree(m->d_all);
     if (m->h_flags) cudaFreeHost(m->h_flags);
+    if (m->h_info) cudaFreeHost(m->h_info);
     delete m;
 }
 
@@ -332,6 +335,53 @@ hd_status hd_mgpu_finish(hd_mgpu *m, uint64_t n_symbols_total, uint64_t *offset,
 }
 
 uint32_t hd_mgpu_repair_count(const hd_mgpu *m) { return m ? m->repairs : 0; }
+
+// End-to-end step from / to HOST memory: this rank's shard goes through the three-stage pipeline of the host decoder
+// (pieces upload, decode and download on three streams: both PCIe directions busy at once), then the triple is
+// exchanged like after hd_mgpu_enqueue.  The context is re-bound to the host decoder's device buffers, so that the rare
+// seam repair of hd_mgpu_finish can run on the device; if it did (hd_mgpu_repair_count() != 0) the caller refreshes its
+// host output with hd_mgpu_host_refresh.
+hd_status hd_mgpu_host_step(hd_mgpu *m, hd_host_decoder *hdec, const uint32_t *h_units, const uint32_t *h_gap_words,
+                            uint8_t *h_out, uint64_t out_cap, void *stream) {
+    if (!m || !hdec || !m->table) return HD_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const hd_mgpu_plan &p = m->plan;
+    uint64_t info[3] = {0, kEmpty, kEmpty};
+    if (p.shard_units) {
+        if (!h_units || !h_out) return HD_ERR_INVALID;
+        hd_status st;
+        if (m->scheme == HD_SCHEME_GAP) {
+            if (!h_gap_words) return HD_ERR_INVALID;
+            const bool from_prev = p.seg_begin != 0;
+            st = hd_host_decode_gap_shard(hdec, h_units, p.readable_units, h_gap_words + (from_prev ? 1 : 0),
+                                          p.seg_end - p.seg_begin, from_prev ? h_gap_words[0] >> 28 : 0u, m->table, h_out,
+                                          out_cap, info, nullptr);
+        } else {
+            st = hd_host_decode_selfsync_shard(hdec, h_units, p.halo_units, p.shard_units, p.readable_units, m->table,
+                                               h_out, out_cap, info, nullptr);
+        }
+        if (st != HD_OK) return st;
+        uint32_t *du = nullptr, *dg = nullptr;
+        uint8_t *dout = nullptr;
+        void *dws = nullptr;
+        hd_host_decoder_buffers(hdec, &du, &dg, &dout, &dws, nullptr);
+        m->d_units = du;
+        m->d_out = dout;
+        m->d_ws = dws;
+    }
+    std::memcpy(m->h_info, info, sizeof(info));
+    MG_CUDA(cudaMemcpyAsync(m->d_info, m->h_info, sizeof(info), cudaMemcpyHostToDevice, s));
+    m->pending = true;
+    return mg_exchange(m, s);
+}
+
+hd_status hd_mgpu_host_refresh(hd_mgpu *m, uint8_t *h_out, uint64_t count, void *stream) {
+    if (!m || !h_out) return HD_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (count) MG_CUDA(cudaMemcpyAsync(h_out, m->d_out, count, cudaMemcpyDeviceToHost, s));
+    MG_CUDA(cudaStreamSynchronize(s));
+    return HD_OK;
+}
 
 hd_status hd_mgpu_infos(const hd_mgpu *m, uint64_t *infos_out) {
     if (!m || !infos_out) return HD_ERR_INVALID;

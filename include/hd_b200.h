@@ -271,6 +271,25 @@ hd_status hd_host_decode_selfsync(hd_host_decoder *h, const uint32_t *units,
 hd_status hd_host_decode_huff(hd_host_decoder *h, const void *file,
                               size_t size, uint8_t *out, size_t out_cap,
                               size_t *out_size, float timing_ms[3]);
+/* One rank's SHARD of a longer stream through the same pipeline (multi-GPU end
+ * to end, see hd_mgpu_host_step).  units -> [left halo | shard | right halo] as
+ * hd_mgpu_plan_shard lays it out; the gap variant takes the shard's own gap
+ * elements and the offset at which its first segment starts.  info_out =
+ * {symbols written to out, entry offset, exit offset}. */
+hd_status hd_host_decode_selfsync_shard(hd_host_decoder *h, const uint32_t *units,
+                                        uint64_t n_units_halo, uint64_t n_units_shard,
+                                        uint64_t n_units_readable, const hd_table *table,
+                                        uint8_t *out, uint64_t out_cap,
+                                        uint64_t info_out[3], float timing_ms[3]);
+hd_status hd_host_decode_gap_shard(hd_host_decoder *h, const uint32_t *units,
+                                   uint64_t n_units_readable, const uint32_t *gap_words,
+                                   uint64_t n_segments, uint32_t entry_bit,
+                                   const hd_table *table, uint8_t *out, uint64_t out_cap,
+                                   uint64_t info_out[3], float timing_ms[3]);
+/* the decoder's device buffers (any pointer may be NULL) */
+void hd_host_decoder_buffers(hd_host_decoder *h, uint32_t **d_units,
+                             uint32_t **d_gap_words, uint8_t **d_out,
+                             void **d_workspace, size_t *workspace_bytes);
 /* one-shot `./bin/demo <gpu> <MB>` shape: allocate, H2D, decode, D2H, free */
 hd_status hd_selfsync_decode_host(const uint32_t *units, uint64_t n_units,
                                   const hd_lut_entry *lut, uint32_t lut_bits,
@@ -464,6 +483,17 @@ hd_status hd_mgpu_enqueue(hd_mgpu *m, void *stream);
 hd_status hd_mgpu_align(hd_mgpu *m, void *stream);
 hd_status hd_mgpu_finish(hd_mgpu *m, uint64_t n_symbols_total, uint64_t *offset,
                          uint64_t *count, void *stream);
+/* End to end from / to HOST memory (the region the reference's multi-GPU demo
+ * times, gpuhd/multigpu_demo.cc:255-313): the rank's shard runs through the
+ * pipelined host decoder (H2D, decode and D2H of pieces overlap), then the
+ * triple is exchanged like after hd_mgpu_enqueue; hd_mgpu_finish follows.  h_*
+ * buffers should be pinned.  After a finish that had to repair this rank
+ * (hd_mgpu_repair_count() != 0, never seen on self-synchronising codes) the
+ * host output is refreshed with hd_mgpu_host_refresh. */
+hd_status hd_mgpu_host_step(hd_mgpu *m, hd_host_decoder *hdec, const uint32_t *h_units,
+                            const uint32_t *h_gap_words, uint8_t *h_out,
+                            uint64_t out_cap, void *stream);
+hd_status hd_mgpu_host_refresh(hd_mgpu *m, uint8_t *h_out, uint64_t count, void *stream);
 /* the triples of the last hd_mgpu_finish (world x 3, host), and how many times
  * THIS rank had to decode again in it (0 in the normal case) */
 hd_status hd_mgpu_infos(const hd_mgpu *m, uint64_t *infos_out);

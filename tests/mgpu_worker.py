@@ -32,6 +32,8 @@ def main():
             d.step()
         placed = d.finish()
         assert sum(c for _, c in placed) == n and d.repairs() == 0
+        e2e = d.e2e(data, steps=2)                            # pinned host shard in/out through hd_mgpu_host_step
+        assert e2e["d2h_bytes_per_step"] == n
         whole = d.gather_output(0)
         if rank == 0:
             assert bool(torch.equal(whole, torch.from_numpy(data).cuda())), "gathered output differs"
