@@ -41,7 +41,7 @@ _lib = None
 
 # every symbol include/hd_b200.h declares (tests check that all are exported)
 ABI_SYMBOLS = [
-    "hd_version", "hd_status_string", "hd_last_cuda_error", "hd_table_from_flat_lut", "hd_table_from_lengths",
+    "hd_version", "hd_status_string", "hd_last_cuda_error", "hd_warmup", "hd_table_from_flat_lut", "hd_table_from_lengths",
     "hd_table_free", "hd_table_max_length", "hd_table_min_length", "hd_workspace_bytes_gap",
     "hd_workspace_bytes_selfsync", "hd_decode_gap", "hd_decode_selfsync", "hd_decode_gap_ex",
     "hd_decode_selfsync_ex", "hd_selfsync_gap_array", "hd_huff_parse", "hd_huff_image_bytes",

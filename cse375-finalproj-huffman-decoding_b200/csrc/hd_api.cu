@@ -393,6 +393,28 @@ const char *hd_status_string(hd_status s) {
 
 const char *hd_last_cuda_error(void) { return cudaGetErrorString(g_last_cuda); }
 
+// Creates the CUDA context of the current device and loads the decode kernels (CUDA loads a kernel's code lazily, at
+// its first launch: tens of milliseconds that would otherwise land inside the first timed decode of a process).
+hd_status hd_warmup(void) {
+    HD_CUDA(cudaFree(nullptr));
+    cudaFuncAttributes a;
+#define HD_TOUCH(k) HD_CUDA(cudaFuncGetAttributes(&a, k))
+#define HD_TOUCH_TILES(L)                                                                                  \
+    HD_TOUCH((hd_decode_tiles_kernel<1, 12, L>)); HD_TOUCH((hd_decode_tiles_kernel<1, 24, L>));            \
+    HD_TOUCH((hd_decode_tiles_kernel<1, 36, L>)); HD_TOUCH((hd_decode_tiles_kernel<2, 12, L>));            \
+    HD_TOUCH((hd_decode_tiles_kernel<2, 24, L>)); HD_TOUCH((hd_decode_tiles_kernel<4, 24, L>));
+    HD_TOUCH_TILES(false)
+    HD_TOUCH_TILES(true)
+    HD_TOUCH((hd_sync_parse_kernel<false, false>)); HD_TOUCH((hd_sync_parse_kernel<false, true>));
+    HD_TOUCH((hd_sync_parse_kernel<true, false>)); HD_TOUCH((hd_sync_parse_kernel<true, true>));
+    HD_TOUCH((hd_sync_walk_kernel<false, false>)); HD_TOUCH((hd_sync_walk_kernel<false, true>));
+    HD_TOUCH((hd_sync_walk_kernel<true, false>)); HD_TOUCH((hd_sync_walk_kernel<true, true>));
+#undef HD_TOUCH_TILES
+#undef HD_TOUCH
+    (void)a;
+    return HD_OK;
+}
+
 // ---------------------------------------------------------------- tables
 static hd_status upload_table(const HostCode &c, void *stream, hd_table **out) {
     hd_table *t = new (std::nothrow) hd_table();

