@@ -404,11 +404,21 @@ class Timer:
         return kern
 
 
-def roofline_of(algo_bytes, step_bytes, k4_ms, step_ms, kern, peak, peak_src):
+def ncu_traffic(mib, r, scheme):
+    """dram__bytes_read.sum + dram__bytes_write.sum of K4 per launch from the committed `ncu --set full` capture of the SAME
+    workload (profiles/k4_traffic.json lists them by workload); None for workloads that were not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k4_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch"].get("%s_%dMiB_r%g" % (scheme, mib, r))
+    except Exception:
+        return None
+
+
+def roofline_of(algo_bytes, step_bytes, k4_ms, step_ms, kern, peak, peak_src, traffic=None):
     achieved = algo_bytes / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else 0.0
     return {"bound": "hbm", "kernel": "hd_decode_tiles_kernel (K4 decode-and-write)", "achieved": round(achieved, 1),
             "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-            "traffic": None,   # not measured in this run: the ncu summaries under profiles/ hold dram bytes per launch
+            "traffic": traffic,   # from the ncu capture of this workload under profiles/ (null: workload not captured)
             "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": round(k4_ms, 4), "peak_source": peak_src,
             "step_roofline_frac": round(step_bytes / (step_ms * 1e-3) / 1e9 / peak, 4),
             "kernels_ms": {k: round(v, 4) for k, v in kern.items() if k != "reserved" and v}}
@@ -446,7 +456,8 @@ def bench_selfsync_1gpu(hd, torch, T, data, units, lut, steps, warmup, clocks=No
     n_seg = (len(units) + 3) // 4
     algo = 4 * len(units) + n + 4 * ((n_seg + 7) // 8)      # K4 reads the gap words K1a left
     step_bytes = 4 * len(units) + n
-    return {"ms": sum(ms) / len(ms), "launches": launches, "kern": kern, "algo": algo, "step_bytes": step_bytes, "parity": parity}
+    return {"ms": sum(ms) / len(ms), "ms_median": float(np.median(ms)), "launches": launches, "kern": kern, "algo": algo,
+            "step_bytes": step_bytes, "parity": parity}
 
 
 def bench_gap_1gpu(hd, torch, T, data, pairs, units, gaps, steps, warmup):
@@ -467,13 +478,16 @@ def bench_gap_1gpu(hd, torch, T, data, pairs, units, gaps, steps, warmup):
     kern = T.kernels(hd, step, None, min(steps, 10))
     table.close()
     algo = 4 * len(units) + n + 4 * len(gaps)
-    return {"ms": sum(ms) / len(ms), "kern": kern, "algo": algo, "step_bytes": algo, "parity": "byte-exact"}
+    return {"ms": sum(ms) / len(ms), "ms_median": float(np.median(ms)), "kern": kern, "algo": algo, "step_bytes": algo,
+            "parity": "byte-exact"}
 
 
 def record(name, scheme, mib, r, res, n, peak, peak_src, input_desc, extra=None):
-    rec = {"config": name, "scheme": scheme, "mib": mib, "redundancy": r, "value": round(n / (res["ms"] * 1e-3) / 1e9, 2),
-           "unit": "GB/s", "ms_per_step": round(res["ms"], 4),
-           "roofline": roofline_of(res["algo"], res["step_bytes"], res["kern"]["decode_write"], res["ms"], res["kern"], peak, peak_src),
+    ms = res["ms_median"]   # (records: median of their few steps; the headline is the mean of exactly K steps)
+    rec = {"config": name, "scheme": scheme, "mib": mib, "redundancy": r, "value": round(n / (ms * 1e-3) / 1e9, 2),
+           "unit": "GB/s", "ms_per_step": round(ms, 4), "ms_per_step_mean": round(res["ms"], 4),
+           "roofline": roofline_of(res["algo"], res["step_bytes"], res["kern"]["decode_write"], ms, res["kern"], peak, peak_src,
+                                   ncu_traffic(mib, r, scheme)),
            "parity": res["parity"], "input": input_desc}
     if extra:
         rec.update(extra)
@@ -530,7 +544,8 @@ def ours(args):
         clk = clocks.stop()
         ms_per_step = res["ms"]
         value = n / (ms_per_step * 1e-3) / 1e9
-        roofline = roofline_of(res["algo"], res["step_bytes"], res["kern"]["decode_write"], ms_per_step, res["kern"], peak, peak_src)
+        roofline = roofline_of(res["algo"], res["step_bytes"], res["kern"]["decode_write"], ms_per_step, res["kern"], peak, peak_src,
+                               ncu_traffic(args.mib, r, "selfsync"))
         launches, parity = res["launches"], res["parity"]
         n_total, n_units_total = n, len(units)
         input_desc = {"data": gen_src, "stream": enc_src}
@@ -654,7 +669,8 @@ def ours(args):
         shard.finish()
         nu, ns = shard.n_units_local, shard.count_local
         algo = 4 * nu + ns + 4 * (((nu + 3) // 4 + 7) // 8)
-        roofline = roofline_of(algo, 4 * nu + ns, kern["decode_write"], ms_per_step, kern, peak, peak_src)
+        roofline = roofline_of(algo, 4 * nu + ns, kern["decode_write"], ms_per_step, kern, peak, peak_src,
+                               ncu_traffic(args.mib, r, "selfsync"))
         parity = "byte-exact (D1-aware on the last symbol)"
         n_units_total = len(units)
         input_desc = {"data": gen_src, "stream": enc_src}
