@@ -20,6 +20,11 @@ while time.time() < t_end:
     # gap scheme, code lengths up to 16
     lim = int(rng.integers(9, 17))
     pairs = hd.build_code(data, lim)
+    if rng.random() < 0.3:      # an INCOMPLETE code (Kraft sum < 1: LUT holes, resolver variants of the kernels): lengthen
+        lens = pairs[:, 1].astype(np.int64)           # some codewords, keep the list order non-decreasing
+        lens = np.minimum(16, lens + rng.integers(0, 3, len(lens)))
+        pairs = pairs.copy()
+        pairs[:, 1] = np.maximum.accumulate(lens).astype(np.uint8)
     units, gaps, bits = hd.encode(data, pairs, want_gaps=True)
     tab = hd.Codetable(pairs=pairs)
     d_units = hd.to_device_units(units)
