@@ -1174,8 +1174,9 @@ static hd_status host_decode_common(hd_host_decoder *h, const uint32_t *units, u
             }
             const uint64_t piece_units = readable_end - b0 * 4;
             Workspace w = carve(h->d_ws, piece_units, false);
+            // (info doubles as the count word and as the {count, entry, exit} triple: a shard reports its exit offset)
             st = run_gap_decode(d_units + b0 * 4, piece_units, d_gaps + s0 / 8, s1 - s0, first_bit, tab, h->d_out,
-                                n_symbols, w, info, h->stream, 0, nullptr, nullptr, false, off_in, info + 3);
+                                n_symbols, w, info, h->stream, 0, nullptr, info, false, off_in, info + 3);
             h->h_flags[i] = 0;
         } else {
             const uint64_t halo = s0 ? std::min<uint64_t>(kHostHaloSegs, b0) / 8 * 8 : base;

@@ -45,6 +45,30 @@ def test_decoder_cli_roundtrip(tmp_path):
 
 
 @pytest.mark.gpu
+def test_encoder_cli_device_path_and_truncated_file(tmp_path):
+    """`bin/encoder --device` (hd_histogram_device + hd_encode_device) writes the same file as the host
+    producer; `bin/decoder` refuses a .huff whose stream holds fewer codewords than its header claims."""
+    enc, dec = _need("encoder"), _need("decoder")
+    data = O.generate(3_000_017, 0.5, seed=15)
+    data.tofile(tmp_path / "in.bin")
+    subprocess.run([enc, str(tmp_path / "in.bin"), str(tmp_path / "host.huff")], check=True, capture_output=True)
+    out = subprocess.run([enc, "--device", str(tmp_path / "in.bin"), str(tmp_path / "dev.huff")], capture_output=True,
+                         text=True, check=True).stdout
+    assert "Device encode kernels" in out and "GB/s of input" in out
+    a, b = np.fromfile(tmp_path / "host.huff", dtype=np.uint8), np.fromfile(tmp_path / "dev.huff", dtype=np.uint8)
+    assert np.array_equal(a, b)
+    assert np.array_equal(O.huff_decode(b, len(data)), data)
+    # claim more decoded bytes than the stream holds: original_size sits behind the 8-byte count and the pair list
+    n_pairs = int(np.frombuffer(b[:8].tobytes(), dtype=np.uint64)[0])
+    bad = b.copy()
+    off = 8 + 2 * n_pairs
+    bad[off:off + 4] = np.frombuffer(np.uint32(len(data) + 4096).tobytes(), dtype=np.uint8)
+    bad.tofile(tmp_path / "bad.huff")
+    run = subprocess.run([dec, str(tmp_path / "bad.huff"), str(tmp_path / "bad.out")], capture_output=True, text=True)
+    assert run.returncode != 0 and not (tmp_path / "bad.out").exists()
+
+
+@pytest.mark.gpu
 def test_demo_cli_shapes(tmp_path):
     demo, mg = _need("demo"), _need("multigpu_demo")
     work = tmp_path / "run"

@@ -458,6 +458,57 @@ def test_gap_shards_through_hd_mgpu(hd, torch_cuda, world, r):
     assert np.array_equal(whole, want)
 
 
+def test_host_decoder_shard_entries(hd, torch_cuda):
+    """hd_host_decode_selfsync_shard / hd_host_decode_gap_shard (the per-rank pipeline of hd_mgpu_host_step) on the
+    middle shard of a three-way split: bytes == the matching slice of the original, triple == what the device path
+    reports for the same shard."""
+    import ctypes as C
+    torch = torch_cuda
+    L = hd.lib()
+    n = 30_000_019
+    data = O.generate(n, 0.5, seed=52)
+    for scheme in (hd.SCHEME_SELFSYNC, hd.SCHEME_GAP):
+        if scheme == hd.SCHEME_SELFSYNC:
+            pairs = hd.build_code(data, 11)
+            units, _ = hd.encode(data, pairs, pad_unit=True)
+            tab = hd.Codetable(flat_lut=hd.flat_lut(pairs, 11))
+            gaps = None
+        else:
+            pairs = hd.build_code(data, 16)
+            units, gaps, _ = hd.encode(data, pairs, want_gaps=True)
+            tab = hd.Codetable(pairs=pairs)
+        # reference: the device path of the same layer, three ranks emulated by threads
+        make = ((lambda r, ag: hd.ShardedSelfSyncDecoder(units, tab, n, r, 3, dist=None, allgather=ag)) if gaps is None else
+                (lambda r, ag: hd.ShardedGapDecoder(units, gaps, tab, n, r, 3, dist=None, allgather=ag)))
+        whole, infos, placed, repairs = _run_ranks(torch, 3, make)
+        assert np.array_equal(whole, data)
+        p = hd.plan_shard(scheme, len(units), 1, 3, max(1, tab.min_length))
+        h_units = torch.from_numpy(np.ascontiguousarray(units[p.first_unit:p.first_unit + p.readable_units]).view(np.int32)).pin_memory()
+        cap = int(p.out_capacity)
+        h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+        hdec = hd.HostDecoder(int(p.readable_units), cap, device=0)
+        info = (C.c_uint64 * 3)()
+        if gaps is None:
+            st = L.hd_host_decode_selfsync_shard(hdec.handle, h_units.data_ptr(), int(p.halo_units), int(p.shard_units),
+                                                 int(p.readable_units), tab.handle, h_out.data_ptr(), cap, info, None)
+        else:
+            gw = np.ascontiguousarray(gaps[p.first_gap_word:p.first_gap_word + p.n_gap_words])
+            st = L.hd_host_decode_gap_shard(hdec.handle, h_units.data_ptr(), int(p.readable_units), gw[1:].ctypes.data,
+                                            int(p.seg_end - p.seg_begin), int(gw[0] >> 28), tab.handle, h_out.data_ptr(),
+                                            cap, info, None)
+        assert st == 0
+        off, cnt = placed[1]
+        assert int(info[0]) == int(infos[1][0]) == cnt
+        assert int(info[1]) == int(infos[1][1]) & 0xffff and int(info[2]) == int(infos[1][2])
+        assert np.array_equal(h_out.numpy()[:cnt], data[off:off + cnt])
+        hdec.close()
+        tab.close()
+
+
+def test_warmup_entry(hd, torch_cuda):
+    assert hd.lib().hd_warmup() == 0
+
+
 def test_host_decoder_selfsync_and_huff(hd, torch_cuda):
     torch = torch_cuda
     n = 3_000_001
