@@ -311,8 +311,9 @@ hd_status hd_selfsync_decode_host(const uint32_t *units, uint64_t n_units,
 #define HD_PROFILE_DECODE_WRITE 2  /* K4 */
 #define HD_PROFILE_SLOTS 4
 /* Tuning knob for benchmarks: 128-bit segments decoded per thread (1, 2 or 4)
- * and decode threads per tile (256 or 512) of the decode-and-write kernel;
- * 0, 0 = automatic (largest tile that fits the SM's shared memory). */
+ * and decode threads per CTA (a multiple of 32, at most 864 = 27 warps) of the
+ * decode-and-write kernel; 0, 0 = automatic (two segments per thread when at
+ * least 20 decode warps fit into the SM's shared memory, else one). */
 void hd_set_tuning(int segs_per_thread, int threads_per_tile);
 /* Developer aid: device buffer (48 x 8 u64) that receives per-step %globaltimer
  * stamps of one CTA of the decode-and-write kernel; NULL switches it off. */
