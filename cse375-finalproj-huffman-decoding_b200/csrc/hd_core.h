@@ -212,7 +212,7 @@ HD_HD uint32_t decode_chunk(const uint32_t *in_col, uint32_t entry, uint32_t sto
             "@p mad.lo.u32 %1, %2, %5, 0;\n\t"    // P = hi
             "}"
             : "+r"(R), "+r"(P)
-            : "r"(hi), "r"(n8n), "r"(n8), "r"(T.one), "n"(NT * 4)
+            : "r"(hi), "r"(n8n), "r"(n8), "r"(T.one), "n"((HD_WHATIF & 64) ? 4 : NT * 4)   // (64: lane-contiguous stores, timing experiment)
             : "memory");
 #else
         if ((n8n ^ n8) & 32u) {

@@ -322,7 +322,8 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
                 smem_st_u32(col_abs + (4 * SEGS + 0) * kWarpRowBytes, pf_la.x, nullptr);
                 smem_st_u32(col_abs + (4 * SEGS + 1) * kWarpRowBytes, pf_la.y, nullptr);
                 if (HD_WHATIF & 4) cnt = 43u;   // (timing experiment: no decode loop)
-                else cnt = decode_chunk<32, LONG>(col, pf_entry, pf_stop, T, stage0_abs + b * stage_bytes + lane * 4u, nullptr);
+                else cnt = decode_chunk<32, LONG>(col, pf_entry, pf_stop, T,
+                                                  stage0_abs + b * stage_bytes + ((HD_WHATIF & 64) ? ((lane * 43u) & ~3u) : lane * 4u), nullptr);
             }
             // ---------------- warp-wide inclusive scan of the counts ----------------
             incl = cnt;
