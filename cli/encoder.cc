@@ -1,9 +1,9 @@
 // encoder.cc -- `./bin/encoder [--device] <input> <output.huff>`
 // CLI shape of the reference gap-array encoder (Huffman_coding_Gap_arrays/encoder/src/huff.cpp:31-34, 176-202); a
 // producer of the same .huff container (<=16-bit length-limited canonical code, 4-bit gap per 128-bit segment).
-// Default: the library's host producer.  --device: histogram, bit packing and gap array run on the GPU
-// (hd_histogram_device / hd_encode_device, replacing encoder.cu:33-116, 142-379; the code itself is a package-merge over
-// the 256-bin histogram on the host) and the device time of those kernels is printed next to the total.
+// Default: the library's host producer.  --device: histogram, length-limited code construction, bit packing and gap
+// array all run on the GPU (hd_encode_device_auto, replacing encoder.cu:33-116, 142-379 and the host package-merge of
+// package_merge.cpp:107-182) and the device time of those kernels is printed next to the total.
 // Input side only -- not the hot path (component 7; section 8(f) row 2).
 #include <cuda_runtime.h>
 #include <hd_b200.h>
@@ -25,41 +25,39 @@
         if (st__ != HD_OK) { std::fprintf(stderr, "%s: %s (%s)\n", #call, hd_status_string(st__), hd_last_cuda_error()); return EXIT_FAILURE; } \
     } while (0)
 
-// histogram -> (host) length-limited code -> pack + gap array, all payload work on the GPU
+// histogram -> length-limited canonical code (kernel) -> pack + gap array: everything on the GPU, one call
 static int encode_on_device(const std::vector<uint8_t> &data, hd_sym_len *pairs, uint32_t *n_pairs, std::vector<uint32_t> &units,
                             std::vector<uint32_t> &gaps, uint32_t *n_units, uint32_t *n_seg, float *kernel_ms) {
     const uint64_t n = data.size();
     uint8_t *d_data = nullptr;
-    uint64_t *d_hist = nullptr, *d_bits = nullptr;
     uint32_t *d_units = nullptr, *d_gaps = nullptr;
+    uint8_t *d_meta = nullptr;   // [0,512): pairs, [512,516): n_pairs, [520,528): total bits
     void *d_ws = nullptr;
-    const uint64_t cap_units = n * 16 / 32 + 8, cap_gaps = (cap_units / 4 + 8) / 8 + 8;
-    const size_t ws_bytes = hd_workspace_bytes_encode(n);
+    const uint64_t cap_units = n * 9 / 32 + 16, cap_gaps = (cap_units / 4 + 8) / 8 + 8;
+    const size_t ws_bytes = (hd_workspace_bytes_encode(n) + 63) / 64 * 64 + 2048 + hd_workspace_bytes_code();
     DEV_CHECK(cudaMalloc(reinterpret_cast<void **>(&d_data), n + 64));
-    DEV_CHECK(cudaMalloc(reinterpret_cast<void **>(&d_hist), 256 * sizeof(uint64_t) + sizeof(uint64_t)));
-    d_bits = d_hist + 256;
+    DEV_CHECK(cudaMalloc(reinterpret_cast<void **>(&d_meta), 1024));
+    DEV_CHECK(cudaMemset(d_meta, 0, 1024));
     DEV_CHECK(cudaMalloc(reinterpret_cast<void **>(&d_units), cap_units * 4));
     DEV_CHECK(cudaMalloc(reinterpret_cast<void **>(&d_gaps), cap_gaps * 4));
     DEV_CHECK(cudaMalloc(&d_ws, ws_bytes));
     DEV_CHECK(cudaMemcpy(d_data, data.data(), n, cudaMemcpyHostToDevice));
-    cudaEvent_t ev[4];
+    cudaEvent_t ev[2];
     for (auto &e : ev) DEV_CHECK(cudaEventCreate(&e));
-    uint64_t hist[256];
     DEV_CHECK(cudaEventRecord(ev[0]));
-    HD_CHECK(hd_histogram_device(d_data, n, d_hist, nullptr));
+    HD_CHECK(hd_encode_device_auto(d_data, n, 16, reinterpret_cast<hd_sym_len *>(d_meta), reinterpret_cast<uint32_t *>(d_meta + 512),
+                                   d_units, cap_units, d_gaps, cap_gaps, d_ws, ws_bytes, reinterpret_cast<uint64_t *>(d_meta + 520),
+                                   nullptr));
     DEV_CHECK(cudaEventRecord(ev[1]));
-    DEV_CHECK(cudaMemcpy(hist, d_hist, sizeof(hist), cudaMemcpyDeviceToHost));
-    HD_CHECK(hd_build_code_from_histogram(hist, 16, pairs, n_pairs));
-    DEV_CHECK(cudaEventRecord(ev[2]));
-    HD_CHECK(hd_encode_device(d_data, n, pairs, *n_pairs, d_units, cap_units, d_gaps, cap_gaps, d_ws, ws_bytes, d_bits, nullptr));
-    DEV_CHECK(cudaEventRecord(ev[3]));
-    DEV_CHECK(cudaEventSynchronize(ev[3]));
-    float a = 0.f, b = 0.f;
-    DEV_CHECK(cudaEventElapsedTime(&a, ev[0], ev[1]));
-    DEV_CHECK(cudaEventElapsedTime(&b, ev[2], ev[3]));
-    *kernel_ms = a + b;
+    DEV_CHECK(cudaEventSynchronize(ev[1]));
+    DEV_CHECK(cudaEventElapsedTime(kernel_ms, ev[0], ev[1]));
+    uint8_t meta[528];
+    DEV_CHECK(cudaMemcpy(meta, d_meta, sizeof(meta), cudaMemcpyDeviceToHost));
     uint64_t bits = 0;
-    DEV_CHECK(cudaMemcpy(&bits, d_bits, sizeof(bits), cudaMemcpyDeviceToHost));
+    std::memcpy(n_pairs, meta + 512, 4);
+    std::memcpy(&bits, meta + 520, 8);
+    if (*n_pairs == 0 || *n_pairs > 256) { std::fprintf(stderr, "cannot build a code for this input\n"); return 1; }
+    std::memcpy(pairs, meta, *n_pairs * sizeof(hd_sym_len));
     *n_units = (uint32_t)((bits + 31) / 32);
     *n_seg = (uint32_t)((bits + 127) / 128);
     units.assign(*n_units ? *n_units : 1, 0);
@@ -67,7 +65,7 @@ static int encode_on_device(const std::vector<uint8_t> &data, hd_sym_len *pairs,
     DEV_CHECK(cudaMemcpy(units.data(), d_units, (size_t)*n_units * 4, cudaMemcpyDeviceToHost));
     DEV_CHECK(cudaMemcpy(gaps.data(), d_gaps, (size_t)((*n_seg + 7) / 8) * 4, cudaMemcpyDeviceToHost));
     for (auto &e : ev) cudaEventDestroy(e);
-    cudaFree(d_data); cudaFree(d_hist); cudaFree(d_units); cudaFree(d_gaps); cudaFree(d_ws);
+    cudaFree(d_data); cudaFree(d_meta); cudaFree(d_units); cudaFree(d_gaps); cudaFree(d_ws);
     return 0;
 }
 
@@ -130,7 +128,7 @@ int main(int argc, char **argv) {
     std::printf("Original size: %u bytes\n", (unsigned)n);
     std::printf("Compressed size: %u bytes\n", n_units * 4);
     if (on_device)
-        std::printf("Device encode kernels (histogram + pack + gap array): %.3f ms = %.2f GB/s of input\n", kernel_ms,
+        std::printf("Device encode kernels (histogram + code + pack + gap array): %.3f ms = %.2f GB/s of input\n", kernel_ms,
                     kernel_ms > 0 ? (double)n / (kernel_ms * 1e-3) / 1e9 : 0.0);
     std::printf("Total encode time: %.3f ms\n", ms);
     std::printf("Throughput: %.2f MB/s\n", (double)n / (1024.0 * 1024.0) / (ms / 1000.0));

@@ -56,6 +56,7 @@ ABI_SYMBOLS = [
     "hd_mailbox_destroy", "hd_decode_gap_shard", "hd_mgpu_plan_shard", "hd_mgpu_first_bad_seam", "hd_mgpu_place",
     "hd_mgpu_create", "hd_mgpu_destroy", "hd_mgpu_exchange_mailbox", "hd_mgpu_exchange_nccl",
     "hd_mgpu_exchange_callback", "hd_mgpu_bind", "hd_mgpu_enqueue", "hd_mgpu_align", "hd_mgpu_finish", "hd_mgpu_infos",
+    "hd_workspace_bytes_code", "hd_build_code_device", "hd_encode_device_auto",
     "hd_mgpu_repair_count", "hd_mgpu_host_step", "hd_mgpu_host_refresh", "hd_host_decode_selfsync_shard",
     "hd_host_decode_gap_shard", "hd_host_decoder_buffers",
 ]
@@ -133,6 +134,9 @@ def lib():
     L.hd_histogram_device.argtypes = [vp, u64, vp, vp]
     L.hd_build_code_from_histogram.argtypes = [vp, u32, vp, C.POINTER(u32)]
     L.hd_encode_device.argtypes = [vp, u64, vp, u32, vp, u64, vp, u64, vp, sz, vp, vp]
+    L.hd_workspace_bytes_code.restype = sz
+    L.hd_build_code_device.argtypes = [vp, u32, vp, vp, vp, vp, sz, vp]
+    L.hd_encode_device_auto.argtypes = [vp, u64, u32, vp, vp, vp, u64, vp, u64, vp, sz, vp, vp]
     L.hd_set_tuning.argtypes = [C.c_int, C.c_int]
     L.hd_set_tuning.restype = None
     L.hd_set_trace.argtypes = [vp]
@@ -527,4 +531,32 @@ def encode_device(d_data, max_len, pad_unit=False):
                                   _stream_ptr(torch)), "hd_encode_device")
     torch.cuda.current_stream().synchronize()
     assert int(d_bits.item()) == bits
+    return pairs, d_units[:n_units + (1 if pad_unit else 0)], d_gaps[:(n_seg + 7) // 8], bits
+
+
+def encode_device_auto(d_data, max_len, pad_unit=False):
+    """The whole producer on the GPU without the host in the loop (hd_encode_device_auto: histogram -> length-limited
+    canonical code built by a kernel -> pack + gap array); only the 256-pair header list and the bit count are read back
+    afterwards.  Returns what encode_device returns."""
+    torch = _torch()
+    n = d_data.numel()
+    cap_units = n * 9 // 32 + 16 if max_len >= 9 else n * max_len // 32 + 16      # a length-limited Huffman code averages < 9 bits
+    d_units = torch.empty(cap_units, dtype=torch.int32, device="cuda")
+    d_gaps = torch.empty((cap_units // 4 + 8) // 8 + 8, dtype=torch.int32, device="cuda")
+    enc_bytes = (lib().hd_workspace_bytes_encode(n) + 63) // 64 * 64
+    nbytes = enc_bytes + 2048 + lib().hd_workspace_bytes_code()
+    ws = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
+    ws_ptr = ws.data_ptr() + (-ws.data_ptr()) % 64
+    d_pairs = torch.zeros(512, dtype=torch.uint8, device="cuda")
+    d_meta = torch.zeros(2, dtype=torch.int64, device="cuda")      # [n_pairs (u32), total bits]
+    _check(lib().hd_encode_device_auto(d_data.data_ptr(), n, max_len, d_pairs.data_ptr(), d_meta.data_ptr(),
+                                       d_units.data_ptr(), cap_units, d_gaps.data_ptr(), d_gaps.numel(), ws_ptr, nbytes,
+                                       d_meta.data_ptr() + 8, _stream_ptr(torch)), "hd_encode_device_auto")
+    meta = d_meta.cpu().numpy()
+    k, bits = int(meta[0]) & 0xffffffff, int(meta[1])
+    if k == 0:
+        raise HDError("hd_encode_device_auto: no code for this input (empty, or more symbols than 2^max_len)")
+    pairs = d_pairs.cpu().numpy()[:2 * k].reshape(-1, 2).copy()
+    n_units = (bits + 31) // 32
+    n_seg = (bits + 127) // 128
     return pairs, d_units[:n_units + (1 if pad_unit else 0)], d_gaps[:(n_seg + 7) // 8], bits

@@ -785,6 +785,30 @@ hd_status hd_histogram_device(const uint8_t *d_data, uint64_t n, uint64_t *d_his
     return HD_OK;
 }
 
+// shared tail of the two encode entries: the code table {code | len << 24} x 256 is already at ws + 64
+static hd_status encode_launch(const uint8_t *d_data, uint64_t n, uint32_t *d_units, uint64_t cap_units, uint32_t *d_gap_words,
+                               uint64_t cap_gap_words, uint8_t *ws, uint64_t *d_bits_out, cudaStream_t s) {
+    EncodeParams p;
+    p.data = d_data;
+    p.n = n;
+    p.tile_counter = reinterpret_cast<uint32_t *>(ws);
+    p.code_tab = reinterpret_cast<uint32_t *>(ws + 64);
+    p.tile_status = reinterpret_cast<uint64_t *>(ws + 64 + 1024);
+    p.units = d_units;
+    p.cap_units = cap_units;
+    p.gap_words = d_gap_words;
+    p.n_tiles = div_up(n, kEncTileSyms);
+    p.bits_out = d_bits_out;
+    HD_CUDA(cudaMemsetAsync(d_units, 0, cap_units * 4, s));
+    if (d_gap_words) HD_CUDA(cudaMemsetAsync(d_gap_words, 0, cap_gap_words * 4, s));
+    const DeviceInfo di = device_info();
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)di.sm_count * 4, p.n_tiles);   // all resident: look-back spins
+    hd_encode_kernel<<<grid, kEncThreads, 0, s>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
 hd_status hd_encode_device(const uint8_t *d_data, uint64_t n, const hd_sym_len *pairs, uint32_t n_pairs,
                            uint32_t *d_units, uint64_t cap_units, uint32_t *d_gap_words, uint64_t cap_gap_words,
                            void *d_workspace, size_t workspace_bytes, uint64_t *d_bits_out, void *stream) {
@@ -797,28 +821,50 @@ hd_status hd_encode_device(const uint8_t *d_data, uint64_t n, const hd_sym_len *
     for (int i = 0; i < 256; ++i) tab[i] = c.len[i] ? (c.code[i] | ((uint32_t)c.len[i] << 24)) : 0u;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     uint8_t *ws = static_cast<uint8_t *>(d_workspace);
-    EncodeParams p;
-    p.data = d_data;
-    p.n = n;
-    p.tile_counter = reinterpret_cast<uint32_t *>(ws);
-    p.code_tab = reinterpret_cast<uint32_t *>(ws + 64);
-    p.tile_status = reinterpret_cast<uint64_t *>(ws + 64 + 1024);
-    p.units = d_units;
-    p.cap_units = cap_units;
-    p.gap_words = d_gap_words;
-    p.n_tiles = div_up(n, kEncTileSyms);
-    p.bits_out = d_bits_out;
     HD_CUDA(cudaMemsetAsync(ws, 0, hd_workspace_bytes_encode(n), s));
     HD_CUDA(cudaMemcpyAsync(ws + 64, tab, sizeof(tab), cudaMemcpyHostToDevice, s));
     HD_CUDA(cudaStreamSynchronize(s));   // `tab` lives on this stack frame
-    HD_CUDA(cudaMemsetAsync(d_units, 0, cap_units * 4, s));
-    if (d_gap_words) HD_CUDA(cudaMemsetAsync(d_gap_words, 0, cap_gap_words * 4, s));
-    const DeviceInfo di = device_info();
-    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)di.sm_count * 4, p.n_tiles);   // all resident: look-back spins
-    hd_encode_kernel<<<grid, kEncThreads, 0, s>>>(p);
+    return encode_launch(d_data, n, d_units, cap_units, d_gap_words, cap_gap_words, ws, d_bits_out, s);
+}
+
+// The whole producer without the host: histogram (already in d_hist256) -> length-limited canonical code built by a
+// kernel (E0) -> pack + gap array.  d_pairs_out (256 pairs) / d_n_pairs_out receive the .huff header list; nothing is
+// read back by this call (the caller copies the pairs and the bit count when it writes the container).
+size_t hd_workspace_bytes_code(void) { return sizeof(CodeScratch) + 64; }
+
+hd_status hd_build_code_device(const uint64_t *d_hist256, uint32_t max_len, hd_sym_len *d_pairs_out, uint32_t *d_n_pairs_out,
+                               uint32_t *d_code_tab256, void *d_scratch, size_t scratch_bytes, void *stream) {
+    if (!d_hist256 || !d_pairs_out || !d_n_pairs_out || !d_code_tab256 || !d_scratch || max_len == 0 || max_len > kMaxCodeLen)
+        return HD_ERR_INVALID;
+    if (scratch_bytes < hd_workspace_bytes_code()) return HD_ERR_WORKSPACE;
+    uintptr_t a = (reinterpret_cast<uintptr_t>(d_scratch) + 63u) & ~(uintptr_t)63u;
+    hd_build_code_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const unsigned long long *>(d_hist256), max_len, d_pairs_out, d_n_pairs_out, d_code_tab256,
+        reinterpret_cast<CodeScratch *>(a));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     HD_CUDA(cudaGetLastError());
     return HD_OK;
+}
+
+hd_status hd_encode_device_auto(const uint8_t *d_data, uint64_t n, uint32_t max_len, hd_sym_len *d_pairs_out,
+                                uint32_t *d_n_pairs_out, uint32_t *d_units, uint64_t cap_units, uint32_t *d_gap_words,
+                                uint64_t cap_gap_words, void *d_workspace, size_t workspace_bytes, uint64_t *d_bits_out,
+                                void *stream) {
+    if (!d_data || !d_pairs_out || !d_n_pairs_out || !d_units || !d_workspace || n == 0 || cap_units == 0) return HD_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(d_data) & 15u) || (reinterpret_cast<uintptr_t>(d_workspace) & 63u)) return HD_ERR_INVALID;
+    const size_t enc_bytes = align_up(hd_workspace_bytes_encode(n), 64);
+    if (workspace_bytes < enc_bytes + 256 * sizeof(uint64_t) + hd_workspace_bytes_code()) return HD_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint8_t *ws = static_cast<uint8_t *>(d_workspace);
+    uint64_t *d_hist = reinterpret_cast<uint64_t *>(ws + enc_bytes);
+    void *d_scratch = ws + enc_bytes + 256 * sizeof(uint64_t);
+    HD_CUDA(cudaMemsetAsync(ws, 0, hd_workspace_bytes_encode(n), s));
+    hd_status st = hd_histogram_device(d_data, n, d_hist, stream);
+    if (st != HD_OK) return st;
+    st = hd_build_code_device(d_hist, max_len, d_pairs_out, d_n_pairs_out, reinterpret_cast<uint32_t *>(ws + 64), d_scratch,
+                              hd_workspace_bytes_code(), stream);
+    if (st != HD_OK) return st;
+    return encode_launch(d_data, n, d_units, cap_units, d_gap_words, cap_gap_words, ws, d_bits_out, s);
 }
 
 // ------------------------------------------------------ multi-GPU mailbox (peer-memory exchange over NVLink)

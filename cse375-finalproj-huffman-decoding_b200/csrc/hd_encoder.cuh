@@ -46,6 +46,87 @@ __global__ void __launch_bounds__(256) hd_histogram_kernel(const uint8_t *data, 
     if (sum) atomicAdd(hist + t, (unsigned long long)sum);
 }
 
+// E0: length-limited code construction ON THE DEVICE from the 256-bin histogram (replaces the host-side boundary
+// package-merge of Huffman_coding_Gap_arrays/encoder/src/package_merge.cpp:107-182 and the sort of
+// encoder/src/huff.cpp:189-194): one CTA; the symbols are rank-sorted in parallel, the package-merge lists (<= 2n items
+// per level, 16 levels) are built level by level by one thread -- 256 symbols are a few thousand steps -- and the
+// {symbol, length} list comes out in the .huff header order (non-decreasing length, most frequent first).  It also
+// writes the encoder's code table {code | len << 24} so that nothing of the code has to visit the host.  Same tie
+// rules as hd_build_code_from_histogram (csrc/hd_host.cpp): the results are identical.
+constexpr uint32_t kCodeMaxItems = 512;   // a package-merge list holds < 2 * 256 items
+struct CodeScratch {                      // global scratch of the kernel (hd_workspace_bytes_code)
+    unsigned long long w[kMaxCodeLen][kCodeMaxItems];
+    uint8_t pkg[kMaxCodeLen][kCodeMaxItems];
+    uint32_t size[kMaxCodeLen];
+};
+
+__global__ void __launch_bounds__(256) hd_build_code_kernel(const unsigned long long *hist, uint32_t max_len, hd_sym_len *pairs_out,
+                                                            uint32_t *n_pairs_out, uint32_t *code_tab, CodeScratch *sc) {
+    __shared__ unsigned long long s_w[256];    // weights of the present symbols, ascending
+    __shared__ uint8_t s_sym[256];             // ... and their symbols
+    __shared__ uint32_t s_len[256];
+    __shared__ uint32_t s_n;
+    const uint32_t t = threadIdx.x;
+    if (t == 0) s_n = 0;
+    __syncthreads();
+    // rank sort by (count ascending, symbol descending): rank = number of present symbols that sort before this one
+    const unsigned long long mine = hist[t];
+    if (mine) {
+        uint32_t rank = 0;
+        for (uint32_t o = 0; o < 256; ++o) {
+            const unsigned long long h = hist[o];
+            if (h && (h < mine || (h == mine && o > t))) ++rank;
+        }
+        s_w[rank] = mine;
+        s_sym[rank] = (uint8_t)t;
+        atomicAdd(&s_n, 1u);
+    }
+    if (t < 256) code_tab[t] = 0;
+    __syncthreads();
+    if (t != 0) return;
+    const uint32_t n = s_n;
+    if (n == 0 || max_len == 0 || max_len > kMaxCodeLen || (1u << max_len) < n) { *n_pairs_out = 0; return; }
+    for (uint32_t i = 0; i < n; ++i) s_len[i] = 0;
+    if (n == 1) {
+        s_len[0] = 1;
+    } else {
+        for (uint32_t l = 0; l < max_len; ++l) {
+            // packages of the previous level, merged with the items (items first on ties)
+            const uint32_t n_pk = l ? sc->size[l - 1] / 2 : 0;
+            uint32_t a = 0, b = 0, k = 0;
+            while (a < n || b < n_pk) {
+                const unsigned long long pw = b < n_pk ? sc->w[l - 1][2 * b] + sc->w[l - 1][2 * b + 1] : 0ull;
+                if (b >= n_pk || (a < n && s_w[a] <= pw)) { sc->w[l][k] = s_w[a++]; sc->pkg[l][k] = 0; }
+                else { sc->w[l][k] = pw; sc->pkg[l][k] = 1; ++b; }
+                ++k;
+            }
+            sc->size[l] = k;
+        }
+        uint32_t take = 2 * n - 2;
+        for (int l = (int)max_len - 1; l >= 0 && take > 0; --l) {
+            if (take > sc->size[l]) take = sc->size[l];
+            uint32_t items = 0, pkgs = 0;
+            for (uint32_t j = 0; j < take; ++j) (sc->pkg[l][j] ? pkgs : items)++;
+            for (uint32_t j = 0; j < items; ++j) s_len[j]++;
+            take = 2 * pkgs;
+        }
+    }
+    // header order: most frequent first, then a stable sort by length = counting sort over the lengths
+    uint32_t k = 0;
+    for (uint32_t len = 1; len <= kMaxCodeLen; ++len)
+        for (uint32_t i = n; i-- > 0;)
+            if (s_len[i] == len) { pairs_out[k].symbol = s_sym[i]; pairs_out[k].length = (uint8_t)len; ++k; }
+    *n_pairs_out = k;
+    // canonical codes in list order (code = (code + 1) << (next_len - len), decoder/src/get_table.cpp:17-20)
+    uint32_t code = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        const uint32_t len = pairs_out[i].length;
+        code_tab[pairs_out[i].symbol] = code | (len << 24);
+        const uint32_t next = i + 1 < k ? pairs_out[i + 1].length : len;
+        code = (code + 1) << (next - len);
+    }
+}
+
 struct EncodeParams {
     const uint8_t *data;
     uint64_t n;

@@ -381,6 +381,29 @@ hd_status hd_encode_device(const uint8_t *d_data, uint64_t n, const hd_sym_len *
                            void *d_workspace, size_t workspace_bytes,
                            uint64_t *d_bits_out, void *stream);
 
+/* The same producer without the host in the loop: hd_build_code_device builds
+ * the length-limited canonical code from a device-resident histogram with a
+ * kernel (replaces the host package-merge, encoder/src/package_merge.cpp:
+ * 107-182, and the header sort of encoder/src/huff.cpp:189-194; identical
+ * result to hd_build_code_from_histogram) and also leaves the encoder's
+ * 256-entry code table {code | len << 24} in d_code_tab256;
+ * hd_encode_device_auto = histogram + code + pack + gap array on one stream,
+ * nothing read back (d_pairs_out: 256 pairs, *d_n_pairs_out: how many; an
+ * unusable histogram -- empty, or more symbols than 2^max_len -- gives 0).
+ * Workspace of _auto: align64(hd_workspace_bytes_encode(n)) + 2048 +
+ * hd_workspace_bytes_code(). */
+size_t hd_workspace_bytes_code(void);
+hd_status hd_build_code_device(const uint64_t *d_hist256, uint32_t max_len,
+                               hd_sym_len *d_pairs_out, uint32_t *d_n_pairs_out,
+                               uint32_t *d_code_tab256, void *d_scratch,
+                               size_t scratch_bytes, void *stream);
+hd_status hd_encode_device_auto(const uint8_t *d_data, uint64_t n, uint32_t max_len,
+                                hd_sym_len *d_pairs_out, uint32_t *d_n_pairs_out,
+                                uint32_t *d_units, uint64_t cap_units,
+                                uint32_t *d_gap_words, uint64_t cap_gap_words,
+                                void *d_workspace, size_t workspace_bytes,
+                                uint64_t *d_bits_out, void *stream);
+
 /* --------------------------------------------------------------- multi GPU
  * Sharding helpers (replace the naive split of gpuhd/multigpu_demo.cc:186-199).
  * Pure host arithmetic: shard `rank` of `world` over n_segments 128-bit

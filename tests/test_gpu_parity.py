@@ -659,6 +659,28 @@ def test_device_encoder_equals_host_encoder(hd, torch_cuda, r, n):
     tab.close()
 
 
+@pytest.mark.parametrize("r,n,max_len", [(0.5, 1_000_003, 16), (0.9, 2_000_000, 16), (0.0, 300_001, 16), (1.0, 77_777, 16),
+                                         (0.5, 500_000, 11), (0.25, 65_537, 9), (0.5, 300, 16)])
+def test_device_code_construction_equals_host(hd, torch_cuda, r, n, max_len):
+    """SURVEY 8(f) row 2, code construction off the host: hd_encode_device_auto (histogram -> package-merge KERNEL ->
+    pack) gives the header list of hd_build_code (host package-merge, itself checked against the oracle's lengths) and
+    the host packer's payload, bit for bit, and the payload decodes back."""
+    torch = torch_cuda
+    data = O.generate(n, r, seed=int(r * 100) + n % 89)
+    pairs, d_units, d_gaps, bits = hd.encode_device_auto(torch.from_numpy(data).cuda(), max_len)
+    pairs_h = hd.build_code(data, max_len)
+    assert np.array_equal(pairs, pairs_h)
+    units_h, gaps_h, bits_h = hd.encode(data, pairs_h, want_gaps=True)
+    assert bits == bits_h
+    assert np.array_equal(d_units.cpu().numpy().view(np.uint32), units_h)
+    assert np.array_equal(d_gaps.cpu().numpy().view(np.uint32), gaps_h)
+    tab = hd.Codetable(pairs=pairs)
+    dec = hd.Decoder(max(d_units.numel(), 1), selfsync=False)
+    out = dec.decode_gap(d_units.contiguous(), d_gaps.contiguous(), tab, n)
+    assert np.array_equal(out.cpu().numpy(), data)
+    tab.close()
+
+
 def test_mailbox_single_rank_roundtrip(hd, torch_cuda):
     """hd_mailbox_* with world 1 (the multi-rank path runs under torchrun in bench.py): publish + wait move the triple
     into the gathered array, sequence numbers gate the wait."""
