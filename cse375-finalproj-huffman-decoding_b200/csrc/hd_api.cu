@@ -75,6 +75,8 @@ struct Workspace {
     uint32_t *changed;       // 8 counters
     uint64_t *count;
     uint32_t *sync_exit;     // self-sync: one published exit word per K1a warp tile (zeroed per call)
+    unsigned long long *tile_map;   // self-sync fallback: transfer function of every K1a tile (16 nibbles)
+    uint8_t *tile_entry;            // self-sync fallback: exact entry offset of every K1a tile
     size_t sync_zero_bytes;  // self-sync: bytes from `changed` on that must be zeroed per call
     uint32_t *gap_words;
     uint8_t *blk_entry;      // per sync chunk: entry offset its landings were parsed from
@@ -91,6 +93,8 @@ size_t ws_bytes(uint64_t n_units, bool selfsync) {
         const uint64_t n_chunks = std::max<uint64_t>(1, div_up(n_seg, kSyncChunkSegs));
         b += align_up((div_up(n_chunks, kSyncTileChunks) + 1) * 4, 64);
         b += align_up(n_chunks * (kSyncChunkSegs / 8) * 4, 64) + align_up(n_chunks, 64);
+        const uint64_t n_sync_tiles = div_up(n_chunks, kSyncTileChunks) + 1;
+        b += align_up(n_sync_tiles * 8, 64) + align_up(n_sync_tiles, 64);
     }
     return b;
 }
@@ -109,6 +113,8 @@ Workspace carve(void *ws, uint64_t n_units, bool selfsync) {
     w.gap_words = nullptr;
     w.blk_entry = nullptr;
     w.sync_exit = nullptr;
+    w.tile_map = nullptr;
+    w.tile_entry = nullptr;
     w.sync_zero_bytes = kCtrlBytes;
     if (selfsync) {
         const uint64_t n_chunks = std::max<uint64_t>(1, div_up(n_seg, kSyncChunkSegs));
@@ -117,6 +123,9 @@ Workspace carve(void *ws, uint64_t n_units, bool selfsync) {
         w.sync_zero_bytes = kCtrlBytes + exit_bytes;
         w.gap_words = reinterpret_cast<uint32_t *>(b + kCtrlBytes + exit_bytes);
         w.blk_entry = b + kCtrlBytes + exit_bytes + align_up(n_chunks * (kSyncChunkSegs / 8) * 4, 64);
+        const uint64_t n_sync_tiles = div_up(n_chunks, kSyncTileChunks) + 1;
+        w.tile_map = reinterpret_cast<unsigned long long *>(w.blk_entry + align_up(n_chunks, 64));
+        w.tile_entry = reinterpret_cast<uint8_t *>(w.tile_map) + align_up(n_sync_tiles * 8, 64);
     }
     return w;
 }
@@ -285,7 +294,8 @@ struct SyncLaunch {
 
 SyncLaunch make_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit, const hd_table *table,
                             uint32_t *d_gap_words, uint8_t *d_cur_entry, uint32_t *d_ctrl, uint64_t n_units_readable,
-                            bool exact, uint32_t *d_sync_exit) {
+                            bool exact, uint32_t *d_sync_exit, unsigned long long *d_tile_map = nullptr,
+                            uint8_t *d_tile_entry = nullptr) {
     SyncLaunch L;
     SyncParams &p = L.p;
     p.units = d_units;
@@ -294,6 +304,9 @@ SyncLaunch make_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_b
     p.n_chunks = div_up(p.n_segments, kSyncChunkSegs);
     p.n_tiles = std::max<uint64_t>(1, div_up(p.n_chunks - 1, kSyncTileChunks));   // tile t owns chunks 31t+1 .. 31t+31 (+ chunk 0)
     p.tile_exit = d_sync_exit;
+    p.tile_map = d_tile_map;
+    p.tile_entry = d_tile_entry;
+    p.use_tile_entry = 0;
     p.first_bit = first_bit;
     p.table = table_dev(table);
     p.gap_words = d_gap_words;
@@ -334,6 +347,26 @@ hd_status launch_sync_walk(const SyncLaunch &L, uint32_t *changed, cudaStream_t 
     return HD_OK;
 }
 
+// second-level fallback: transfer functions of all tiles (K1c), the chase through them, then K1a with exact tile entries
+template <bool EXACT, bool LONG>
+hd_status launch_sync_maps(const SyncLaunch &L, cudaStream_t s) {
+    if (!L.p.tile_map || !L.p.tile_entry) return HD_ERR_UNRESOLVED;
+    HD_CUDA(cudaMemsetAsync(L.p.tile_map, 0, L.p.n_tiles * sizeof(unsigned long long), s));
+    auto kmap = hd_sync_map_kernel<EXACT, LONG>;
+    auto kchase = hd_sync_chase_kernel<EXACT, LONG>;
+    HD_CUDA(cudaFuncSetAttribute(kmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_tables));
+    HD_CUDA(cudaFuncSetAttribute(kchase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_tables));
+    const unsigned grid = (unsigned)div_up(L.p.n_tiles * 16, 256);
+    kmap<<<grid, 256, L.smem_tables, s>>>(L.p);
+    kchase<<<1, 256, L.smem_tables, s>>>(L.p);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    HD_CUDA(cudaGetLastError());
+    SyncLaunch L2 = L;
+    L2.p.use_tile_entry = 1;
+    HD_CUDA(cudaMemsetAsync(L2.p.tile_counter, 0, 4, s));   // K1a's ticket counter
+    return launch_sync_parse<EXACT, LONG>(L2, s);
+}
+
 #define HD_SYNC_DISPATCH(fn, L, ...)                                                               \
     ((L).exact ? ((L).lng ? fn<true, true>((L), __VA_ARGS__) : fn<true, false>((L), __VA_ARGS__))   \
                : ((L).lng ? fn<false, true>((L), __VA_ARGS__) : fn<false, false>((L), __VA_ARGS__)))
@@ -360,7 +393,10 @@ hd_status finish_sync(const SyncLaunch &L, cudaStream_t s, bool *extra_rounds) {
     if (h_changed == 0) return HD_OK;
     *extra_rounds = true;
     uint32_t *changed = L.p.changed + 2;
-    const uint64_t max_rounds = div_up(L.p.n_chunks, kSyncWalkChunks) + 3;
+    // A parse that fails to merge inside one tile usually merges in the next: a few K1b rounds settle it.  A code that
+    // keeps failing (it does not self-synchronise at all) would need one round per tile: the transfer-function pass
+    // resolves every tile at once instead.
+    const uint64_t max_rounds = 3;
     for (uint64_t round = 0; round <= max_rounds; ++round) {
         HD_CUDA(cudaMemsetAsync(changed, 0, 4, s));
         ProfScope prof(HD_PROFILE_SYNC_SEAMS, s);
@@ -370,7 +406,14 @@ hd_status finish_sync(const SyncLaunch &L, cudaStream_t s, bool *extra_rounds) {
         HD_CUDA(cudaStreamSynchronize(s));
         if (h_changed == 0) return HD_OK;
     }
-    return HD_ERR_UNRESOLVED;
+    {
+        ProfScope prof(HD_PROFILE_SYNC_SEAMS, s);
+        hd_status st = L.exact ? (L.lng ? launch_sync_maps<true, true>(L, s) : launch_sync_maps<true, false>(L, s))
+                               : (L.lng ? launch_sync_maps<false, true>(L, s) : launch_sync_maps<false, false>(L, s));
+        if (st != HD_OK) return st;
+    }
+    HD_CUDA(cudaStreamSynchronize(s));
+    return HD_OK;
 }
 
 }  // namespace
@@ -573,7 +616,7 @@ hd_status hd_selfsync_gap_array(const uint32_t *d_units, uint64_t n_units, uint3
     Workspace w = carve(d_workspace, n_units, true);
     HD_CUDA(cudaMemsetAsync(w.changed, 0, w.sync_zero_bytes, s));
     // exact landings: this entry returns a gap array in the .huff sense (first codeword of every segment)
-    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, true, w.sync_exit);
+    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, true, w.sync_exit, w.tile_map, w.tile_entry);
     st = run_sync(L, s);
     if (st != HD_OK) return st;
     bool extra = false;
@@ -605,7 +648,7 @@ hd_status hd_decode_selfsync_enqueue(const uint32_t *d_units, uint64_t n_units, 
     // array after every phase-2 launch, cuhd_gpu_decoder.cu:461-495).  One memset covers K4's ticket counter and
     // tile statuses and, right behind them, K1's control block.
     HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes + w.sync_zero_bytes, s));
-    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, false, w.sync_exit);
+    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, false, w.sync_exit, w.tile_map, w.tile_entry);
     st = run_sync(L, s);
     if (st != HD_OK) return st;
     st = run_gap_decode(d_units, n_units, w.gap_words, n_seg, first_bit, table, d_out, n_symbols, w, d_count, s, 0, nullptr,
@@ -628,7 +671,7 @@ hd_status hd_decode_selfsync_finish(const uint32_t *d_units, uint64_t n_units, u
     if (st != HD_OK) return st;
     if (workspace_bytes < ws_bytes(n_units, true)) return HD_ERR_WORKSPACE;
     Workspace w = carve(d_workspace, n_units, true);
-    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, false, w.sync_exit);
+    const SyncLaunch L = make_sync(d_units, n_units, first_bit, table, w.gap_words, w.blk_entry, w.changed, 0, false, w.sync_exit, w.tile_map, w.tile_entry);
     bool extra = false;
     st = finish_sync(L, s, &extra);
     if (st != HD_OK) return st;
@@ -701,7 +744,7 @@ static hd_status shard_enqueue_impl(const uint32_t *d_units, uint64_t n_units_ha
     Workspace w = carve(d_workspace, n_units, true);
     HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes + w.sync_zero_bytes, s));
     const SyncLaunch L = make_sync(d_units, n_units, n_units_halo ? 0u : first_bit, table, w.gap_words, w.blk_entry,
-                                   w.changed, n_units_readable, false, w.sync_exit);
+                                   w.changed, n_units_readable, false, w.sync_exit, w.tile_map, w.tile_entry);
     st = run_sync(L, s);
     if (st != HD_OK) return st;
     st = shard_decode(d_units, n_units_halo, n_units_shard, n_units_readable, first_bit, table, d_out, out_cap, w,
@@ -735,7 +778,7 @@ hd_status hd_decode_selfsync_shard_finish(const uint32_t *d_units, uint64_t n_un
     const uint64_t n_units = n_units_halo + n_units_shard;
     Workspace w = carve(d_workspace, n_units, true);
     const SyncLaunch L = make_sync(d_units, n_units, n_units_halo ? 0u : first_bit, table, w.gap_words, w.blk_entry,
-                                   w.changed, n_units_readable, false, w.sync_exit);
+                                   w.changed, n_units_readable, false, w.sync_exit, w.tile_map, w.tile_entry);
     bool extra = false;
     st = finish_sync(L, s, &extra);
     if (st != HD_OK) return st;

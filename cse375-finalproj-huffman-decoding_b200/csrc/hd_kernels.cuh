@@ -6,6 +6,8 @@
 //        (replaces phase 1, cuhd_gpu_decoder.cu:145-233)
 //   K1b hd_sync_walk_kernel    : seams between warp tiles, walked to the merge
 //        (replaces phase 2 + host loop, cuhd_gpu_decoder.cu:235-327, 461-495)
+//   K1c hd_sync_map_kernel + hd_sync_chase_kernel : per-tile transfer functions and the chase through them, for codes
+//        that never synchronise (no counterpart in the reference: it emits garbage there)
 //
 // Integer/byte work only: no tensor cores.  See DESIGN.md for the data layout
 // and the per-kernel roofline.
@@ -100,6 +102,10 @@ struct SyncParams {
     uint32_t *changed;           // per-round "some chunk's exit changed" counter
     uint32_t *tile_counter;      // ticket counter of the persistent K1a warps (zeroed before launch)
     uint32_t *tile_exit;         // per K1a warp tile: kExitPublished | offset at which its parse leaves it (zeroed before launch)
+    // second-level fallback (codes that do not synchronise within whole tiles: K1c + chase, then K1a once more):
+    unsigned long long *tile_map;   // per tile: 16 nibbles, nibble x = exit offset of the tile when it is entered at offset x
+    uint8_t *tile_entry;            // per tile: the exact offset at which the true parse enters its first owned chunk
+    uint32_t use_tile_entry;        // K1a: take lane 1's entry from tile_entry instead of speculating (no seam checks)
 };
 constexpr uint32_t kExitPublished = 0x100u;
 constexpr uint32_t kExitWaitPolls = 1u << 16;   // bounded wait for a predecessor tile (then: flag `changed`, K1b rounds decide)
@@ -385,7 +391,8 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
         // round).  After this the tile is consistent given the entry of its FIRST owned chunk; check_seam() looks at that one.
         const TileSegLoader tld{tile, q0};
         for (;;) {
-            const uint32_t left = __shfl_up_sync(0xffffffffu, words[1] >> 28, 1);
+            uint32_t left = __shfl_up_sync(0xffffffffu, words[1] >> 28, 1);
+            if (p.use_tile_entry && lane == 1 && ticket > 0) left = p.tile_entry[ticket];   // exact (chased through the tile maps)
             const bool redo = active && lane > 0 && left != entry && !(HD_WHATIF & 512);
             if (!__any_sync(0xffffffffu, redo)) break;
             if (redo) {
@@ -402,7 +409,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
         }
         const uint32_t assumed = __shfl_sync(0xffffffffu, words[1] >> 28, 0);   // lane 0's exit = what lane 1 was entered with
         check_seam();   // of the tile this warp parsed BEFORE this one
-        if (ticket > 0) { pend_tile = ticket; pend_assumed = assumed; }
+        if (ticket > 0 && !p.use_tile_entry) { pend_tile = ticket; pend_assumed = assumed; }
         __syncwarp();   // the repair above wrote this warp's earlier results; keep the warp together before restaging
     }
     check_seam();
@@ -467,6 +474,81 @@ __global__ void __launch_bounds__(128) hd_sync_walk_kernel(const SyncParams p) {
         xin = words[1] >> 28;
     }
     if (exit_changed) atomicAdd(p.changed, 1u);
+}
+
+// =========================================================================
+// Second-level fallback for codes that do not synchronise within whole tiles (e.g. all codewords 3 bits: the parse of
+// such a code is a sequential chain, and K1b moves it one tile per round).  The chain is turned into a PREFIX problem
+// over TRANSFER FUNCTIONS: the offset at which the parse leaves a tile depends only on the offset (0..15) at which it
+// enters it, so every tile has a map {0..15} -> {0..15}; the maps of all tiles are computed in parallel (K1c: 16 lanes
+// per tile, lane x parses the tile from entry offset x), one thread chases the true entry through them (16 nibbles per
+// tile, staged through shared memory), and K1a runs once more with the exact tile entries.  Any prefix code, no rounds.
+// =========================================================================
+template <bool EXACT, bool LONG>
+__global__ void __launch_bounds__(256) hd_sync_map_kernel(const SyncParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    SyncLut L;
+    sync_stage_tables(p.table, smem, L);
+    __syncthreads();
+    const uint64_t half = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;   // one half warp per tile
+    const uint32_t x = threadIdx.x & 15u;
+    if (half >= p.n_tiles) return;
+    const uint64_t c0 = half * kSyncTileChunks + 1;
+    uint64_t c1 = c0 + kSyncTileChunks;
+    if (c1 > p.n_chunks) c1 = p.n_chunks;
+    uint32_t pos = x;
+    if (c0 < c1) {
+        const GlobalSegLoader ld{p.units, p.n_units};
+        uint64_t s0 = c0 * kSyncChunkSegs, s1 = c1 * kSyncChunkSegs;
+        if (s1 > p.n_segments) s1 = p.n_segments;
+        Seg4 cur = ld(s0);
+        for (uint64_t sg = s0; sg < s1; ++sg) {
+            const Seg4 nxt = ld(sg + 1);
+            pos = sync_segment<EXACT, LONG>(cur.x, cur.y, cur.z, cur.w, nxt.x, pos, L);
+            cur = nxt;
+        }
+    }
+    atomicOr(p.tile_map + half, (unsigned long long)(pos & 15u) << (4u * x));   // (zeroed before launch)
+}
+
+// one CTA: thread 0 parses chunk 0 from the stream's known start, then chases the entry through the tile maps
+template <bool EXACT, bool LONG>
+__global__ void __launch_bounds__(256) hd_sync_chase_kernel(const SyncParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    SyncLut L;
+    sync_stage_tables(p.table, smem, L);
+    __shared__ unsigned long long s_map[2048];
+    __shared__ uint8_t s_entry[2048];
+    __shared__ uint32_t s_x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const GlobalSegLoader ld{p.units, p.n_units};
+        uint32_t pos = p.first_bit;
+        uint64_t s1 = kSyncChunkSegs < p.n_segments ? kSyncChunkSegs : p.n_segments;
+        Seg4 cur = ld(0);
+        for (uint64_t sg = 0; sg < s1; ++sg) {
+            const Seg4 nxt = ld(sg + 1);
+            pos = sync_segment<EXACT, LONG>(cur.x, cur.y, cur.z, cur.w, nxt.x, pos, L);
+            cur = nxt;
+        }
+        s_x = pos & 15u;
+    }
+    for (uint64_t base = 0; base < p.n_tiles; base += 2048) {
+        const uint64_t n = p.n_tiles - base < 2048 ? p.n_tiles - base : 2048;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_map[i] = p.tile_map[base + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t xx = s_x;
+            for (uint32_t i = 0; i < n; ++i) {
+                s_entry[i] = (uint8_t)xx;
+                xx = (uint32_t)(s_map[i] >> (4u * xx)) & 15u;
+            }
+            s_x = xx;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) p.tile_entry[base + i] = s_entry[i];
+    }
 }
 
 }  // namespace hd

@@ -146,6 +146,38 @@ def test_never_synchronising_code(hd, torch_cuda):
     assert cnt == n
 
 
+@pytest.mark.parametrize("length,n", [(3, 60_000_017), (5, 20_000_003), (7, 12_345_678)])
+def test_never_synchronising_code_at_size(hd, torch_cuda, length, n):
+    """The same at sizes with thousands of K1a tiles (60 M symbols of a 3-bit code = 2800 tiles of 64 Kbit): after a few
+    K1b rounds the synchronisation switches to the transfer-function pass (every tile's entry -> exit map in parallel,
+    one chase through the maps, K1a once more with exact tile entries) instead of one round per tile; also the EXACT
+    variant behind hd_selfsync_gap_array, whose result must be the gap array of the stream."""
+    import time
+    torch = torch_cuda
+    k = min(256, 1 << length)
+    pairs = cases.fixed_length_code(k, length)
+    data = hd.generate(n, 0.0, seed=length) % k
+    data = data.astype(np.uint8)
+    units, gaps, bits = hd.encode(data, pairs, want_gaps=True)
+    units = np.concatenate([units, np.zeros(1, dtype=np.uint32)])          # the CUHD pad unit
+    lut = hd.flat_lut(pairs, 11)
+    tab = hd.Codetable(flat_lut=lut)
+    d_units = hd.to_device_units(units)
+    dec = hd.Decoder(d_units.numel(), selfsync=True)
+    dec.decode_selfsync(d_units, tab, n)                                   # (kernels loaded)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    out = dec.decode_selfsync(d_units, tab, n)
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    assert bool(torch.equal(out, torch.from_numpy(data).cuda())) and int(dec.count.item()) == n
+    assert dt < 2.0, "never-synchronising decode took %.2f s" % dt
+    gw = dec.gap_array(d_units, tab).cpu().numpy().view(np.uint32)
+    n_seg = (len(units) - 1 + 3) // 4
+    assert np.array_equal(gw[:(n_seg + 7) // 8 - 1], gaps[:(n_seg + 7) // 8 - 1])   # (the last word also covers the pad unit)
+    tab.close()
+
+
 @pytest.mark.parametrize("length", [1, 2, 4, 5, 7, 8, 11])
 def test_fixed_length_codes(hd, torch_cuda, length):
     k = min(256, 1 << length)
