@@ -19,7 +19,7 @@
 
 namespace {
 
-constexpr uint64_t kSegUnits = 4, kTileSegs = 256, kDefaultHaloSegs = 4096;
+constexpr uint64_t kSegUnits = 4, kDefaultHaloSegs = 4096;
 constexpr uint64_t kEmpty = ~0ull;          // entry / exit of a rank without segments
 constexpr uint64_t kUnconvergedBit = 1ull << 32;
 constexpr int kFlagRing = 256;
@@ -30,18 +30,16 @@ inline uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 // library itself does not link against NCCL
 typedef int (*nccl_allgather_t)(const void *, void *, size_t, int, void *, cudaStream_t);
 nccl_allgather_t find_nccl_allgather() {
-    static nccl_allgather_t fn = nullptr;
-    static bool looked = false;
-    if (looked) return fn;
-    looked = true;
-    void *sym = dlsym(RTLD_DEFAULT, "ncclAllGather");
-    if (!sym) {
-        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
-        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
-        if (!h) h = dlopen("libnccl.so", RTLD_NOW);
-        if (h) sym = dlsym(h, "ncclAllGather");
-    }
-    fn = reinterpret_cast<nccl_allgather_t>(sym);
+    static const nccl_allgather_t fn = [] {   // (resolved once; thread-safe: one host thread per GPU may get here at the same time)
+        void *sym = dlsym(RTLD_DEFAULT, "ncclAllGather");
+        if (!sym) {
+            void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+            if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+            if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+            if (h) sym = dlsym(h, "ncclAllGather");
+        }
+        return reinterpret_cast<nccl_allgather_t>(sym);
+    }();
     return fn;
 }
 constexpr int kNcclUint64 = 5;   // ncclDataType_t ncclUint64 (nccl.h)
