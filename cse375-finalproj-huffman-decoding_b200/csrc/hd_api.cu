@@ -312,6 +312,7 @@ SyncLaunch make_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_b
     p.tile_map = d_tile_map;
     p.tile_entry = d_tile_entry;
     p.use_tile_entry = 0;
+    p.k_one = 1u;
     p.first_bit = first_bit;
     p.table = table_dev(table);
     p.gap_words = d_gap_words;
@@ -319,7 +320,9 @@ SyncLaunch make_sync(const uint32_t *d_units, uint64_t n_units, uint32_t first_b
     p.changed = d_ctrl;
     p.tile_counter = d_ctrl + 8;
     L.smem_tables = sync_smem_bytes(table);
-    L.smem_parse = L.smem_tables + (size_t)kSyncWarps * kSyncTileBytes;
+    // (the decode path's K1a keeps a byte jump table, aligned to its size, instead of the u16 table: see the kernel)
+    const size_t parse_tables = (exact || (HD_WHATIF & 2048)) ? L.smem_tables : (size_t)sync_jump8_tables_bytes(table->host.lut_bits);
+    L.smem_parse = parse_tables + (size_t)kSyncWarps * kSyncTileBytes;
     L.exact = exact;
     L.lng = table->host.has_long != 0;
     return L;

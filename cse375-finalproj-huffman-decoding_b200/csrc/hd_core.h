@@ -343,6 +343,9 @@ HD_HD void column_write_head(uint32_t w0, uint32_t c, uint32_t D, uint8_t *arena
 // ---------------------------------------------------------------- sync side
 struct SyncLut {
     const uint16_t *lut;   // {jump_bits | first_len << 8}
+    uint32_t one = 1;        // the constant 1, opaque to the compiler where it comes from a kernel parameter (see decode_chunk)
+    bool use8 = false;       // optional byte copy of the jumps (K1a, non-EXACT: see hd_sync_parse_kernel); a constant
+    uint32_t jump8_hi = 0;   // per kernel.  jump8_hi = its shared-window address >> lm (it is aligned to its size)
     uint32_t idx_shift;
     uint32_t lm;
     const LongTables *lt;
@@ -373,7 +376,14 @@ struct Seg4 {
 // Merge test of the reference: cuhd_gpu_decoder.cu:208-213.
 template <bool EXACT, bool LONG>
 HD_HD uint32_t sync_step(uint32_t win, uint32_t pos, const SyncLut &L) {
-    uint32_t ent = L.lut[win >> L.idx_shift];
+    uint32_t ent;
+#if defined(__CUDA_ARCH__)
+    if (!EXACT && L.use8) {   // (a compile-time constant of the kernel)
+        // address = table base | index in ONE funnel shift: (base >> lm : win) >> (32 - lm)
+        asm("ld.shared.u8 %0, [%1];" : "=r"(ent) : "r"(__funnelshift_r(win, L.jump8_hi, L.idx_shift)));
+    } else
+#endif
+        ent = L.lut[win >> L.idx_shift];
     if (LONG) {
         if (ent == 0) {
             const uint32_t first = resolve_long(win, L.lm, L.lt, L.order) & 0xffu;
@@ -427,23 +437,82 @@ template <bool EXACT, bool LONG, bool RECORD>
 HD_HD uint32_t sync_run(const uint32_t *words, uint32_t pos, uint32_t end_bits, const SyncLut &L, uint32_t land_addr,
                         uint8_t *arena) {
     uint32_t w0 = words[0], w1 = words[1], w2 = words[2];
+#if defined(__CUDA_ARCH__)
+    uint32_t nxt = (uint32_t)__cvta_generic_to_shared(words + 2);   // shared-window address of the word in w2
+#else
     const uint32_t *nxt = words + 2;
+#endif
+#if defined(__CUDA_ARCH__)
+    uint32_t lp = land_addr + ((pos >> 7) << 5);   // landing slot of the segment that holds `pos`
+#endif
     while (pos < end_bits) {
         const uint32_t win = funnel_l(w1, w0, pos);
         const uint32_t s1 = sync_step<EXACT, LONG>(win, pos & (kSegmentBits - 1u), L);
         const uint32_t p1 = pos + s1;
         const uint32_t s2 = sync_step<EXACT, LONG>(win << s1, p1 & (kSegmentBits - 1u), L);
+#if defined(__CUDA_ARCH__)
+        uint32_t np = p1;   // + s2 unless the first step crossed a segment boundary: one predicated multiply-add
+        asm("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 x;\n\t"
+            "xor.b32 x, %1, %2;\n\t"
+            "and.b32 x, x, 128;\n\t"
+            "setp.ne.u32 p, x, 0;\n\t"
+            "@!p mad.lo.u32 %0, %3, %4, %0;\n\t"
+            "}"
+            : "+r"(np)
+            : "r"(p1), "r"(pos), "r"(s2), "r"(L.one));
+#else
         const uint32_t np = ((p1 ^ pos) & kSegmentBits) ? p1 : p1 + s2;
+#endif
+#if defined(__CUDA_ARCH__)
+        if (RECORD) {
+            // store into the slot of the segment the iteration started in; the slot pointer moves on when the position
+            // crosses into the next segment (a pair of steps is at most 32 bits: never two segments): one logic
+            // instruction + a predicated multiply-add instead of shift, mask and add per iteration
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                ".reg .b32 x;\n\t"
+                "st.shared.u8 [%0], %1;\n\t"
+                "xor.b32 x, %1, %2;\n\t"
+                "and.b32 x, x, 128;\n\t"
+                "setp.ne.u32 p, x, 0;\n\t"
+                "@p mad.lo.u32 %0, %3, 32, %0;\n\t"
+                "}"
+                : "+r"(lp)
+                : "r"(np), "r"(pos), "r"(L.one)
+                : "memory");
+        }
+#else
         if (RECORD) smem_st_u8(land_addr + ((pos >> 7) << 5), np, arena);
+#endif
+#if defined(__CUDA_ARCH__)
+        // Crossed a unit boundary: slide the window and fetch the word after it, as in decode_chunk: one block with
+        // its own predicate, the pointer bumped and the word loaded IN PLACE (written as C the compiler spends two
+        // more predicated moves per iteration on temporaries).
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 x;\n\t"
+            "xor.b32 x, %4, %5;\n\t"
+            "and.b32 x, x, 32;\n\t"
+            "setp.ne.u32 p, x, 0;\n\t"
+            "@p mad.lo.u32 %0, %1, %6, 0;\n\t"   // w0 = w1   (multiply by an opaque 1: IMAD on the FMA pipe, not SEL)
+            "@p mad.lo.u32 %1, %2, %6, 0;\n\t"   // w1 = w2
+            "@p mad.lo.u32 %3, %6, 4, %3;\n\t"   // nxt += 4
+            "@p ld.shared.u32 %2, [%3];\n\t"
+            "}"
+            : "+r"(w0), "+r"(w1), "+r"(w2), "+r"(nxt)
+            : "r"(np), "r"(pos), "r"(L.one));
+#else
         if ((np ^ pos) & 32u) {
             w0 = w1;
             w1 = w2;
             ++nxt;
             w2 = *nxt;
-#if defined(__CUDA_ARCH__)
-            asm volatile("");   // keep predicated moves (FMA pipe) instead of selects (INT pipe), see decode_chunk
-#endif
         }
+#endif
         pos = np;
     }
     return pos;

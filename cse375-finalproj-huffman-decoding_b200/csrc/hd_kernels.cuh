@@ -106,6 +106,7 @@ struct SyncParams {
     unsigned long long *tile_map;   // per tile: 16 nibbles, nibble x = exit offset of the tile when it is entered at offset x
     uint8_t *tile_entry;            // per tile: the exact offset at which the true parse enters its first owned chunk
     uint32_t use_tile_entry;        // K1a: take lane 1's entry from tile_entry instead of speculating (no seam checks)
+    uint32_t k_one;                 // 1 (opaque to ptxas: keeps the window slide of sync_run on the FMA pipe)
 };
 constexpr uint32_t kExitPublished = 0x100u;
 constexpr uint32_t kExitWaitPolls = 1u << 16;   // bounded wait for a predecessor tile (then: flag `changed`, K1b rounds decide)
@@ -248,6 +249,10 @@ __device__ __forceinline__ void sync_stage_tables(const TableDev &tb, uint8_t *s
     L.lt = s_long;
     L.order = s_order;
 }
+// K1a, EXACT = false: [padding < 2^lm][u8 jump[2^lm], aligned to its size][order][LongTables] -- sized for the worst padding
+__host__ __device__ __forceinline__ uint32_t sync_jump8_tables_bytes(uint32_t lut_bits) {
+    return (1u << lut_bits) + (((1u << lut_bits) + 15u) & ~15u) + 256u + (((uint32_t)sizeof(LongTables) + 15u) & ~15u);
+}
 __device__ __forceinline__ uint32_t sync_tables_bytes(uint32_t lut_bits) {
     return (((2u << lut_bits) + 15u) & ~15u) + 256u + (((uint32_t)sizeof(LongTables) + 15u) & ~15u);
 }
@@ -278,10 +283,42 @@ template <bool EXACT, bool LONG>
 __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const SyncParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     SyncLut L;
-    sync_stage_tables(p.table, smem, L);
+    uint32_t tiles_off;
+    if constexpr (!EXACT && !(HD_WHATIF & 2048)) {
+        // The decode path's landing rule (EXACT = false) needs only the jump of an entry: a BYTE table, placed in the
+        // dynamic window at an address that is a multiple of its size, so that the funnel shift that extracts the
+        // window's index bits also ORs in the table's address (the base goes in as the shift's upper word): the load
+        // needs no address arithmetic at all, and four entries share a bank word instead of two.
+        const uint32_t lm = p.table.lut_bits, tsz = 1u << lm;
+        const uint32_t abs0 = (uint32_t)__cvta_generic_to_shared(smem);
+        const uint32_t pad = (0u - abs0) & (tsz - 1u);   // (< tsz; the host sized the window for tsz)
+        uint8_t *s_jump8 = smem + pad;
+        uint8_t *s_order = s_jump8 + ((tsz + 15u) & ~15u);
+        LongTables *s_long = reinterpret_cast<LongTables *>(s_order + 256);
+        const uint16_t *src = reinterpret_cast<const uint16_t *>(p.table.blob + p.table.off_sync);
+        for (uint32_t i = threadIdx.x; i < tsz; i += blockDim.x) s_jump8[i] = (uint8_t)__ldg(src + i);
+        if (p.table.has_long) {
+            for (uint32_t i = threadIdx.x; i < 64; i += blockDim.x)
+                reinterpret_cast<uint32_t *>(s_order)[i] = __ldg(reinterpret_cast<const uint32_t *>(p.table.blob + p.table.off_order) + i);
+            for (uint32_t i = threadIdx.x; i < sizeof(LongTables) / 4; i += blockDim.x)
+                reinterpret_cast<uint32_t *>(s_long)[i] = __ldg(reinterpret_cast<const uint32_t *>(p.table.blob + p.table.off_long) + i);
+        }
+        L.lut = nullptr;
+        L.idx_shift = 32 - lm;
+        L.lm = lm;
+        L.lt = s_long;
+        L.order = s_order;
+        L.use8 = true;
+        L.jump8_hi = (abs0 + pad) >> lm;
+        tiles_off = pad + sync_jump8_tables_bytes(lm) - tsz;
+    } else {
+        sync_stage_tables(p.table, smem, L);
+        tiles_off = sync_tables_bytes(p.table.lut_bits);
+    }
+    L.one = p.k_one;
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4 *tile = reinterpret_cast<uint4 *>(smem + sync_tables_bytes(p.table.lut_bits) + (size_t)warp * kSyncTileBytes);
+    uint4 *tile = reinterpret_cast<uint4 *>(smem + tiles_off + (size_t)warp * kSyncTileBytes);
     const uint32_t land_abs = (uint32_t)__cvta_generic_to_shared(tile + kSyncTilePhysUnits);   // landing bytes [slot][lane]
     const uint64_t n_units16 = (p.n_units + 3) >> 2;   // 16-byte units that hold stream data (last one may be partial)
 
