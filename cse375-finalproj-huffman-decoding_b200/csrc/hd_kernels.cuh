@@ -376,6 +376,26 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
         const int64_t q0 = (int64_t)(chunk0 * kSyncChunkSegs) - kSyncHaloSegs;
         __syncwarp();   // every lane is done reading the previous tile
         const bool interior = q0 >= 0 && (uint64_t)q0 + kSyncTileSrcUnits <= (p.n_units >> 2);   // every unit is whole
+        if (interior && !(HD_WHATIF & 4096)) {
+            // Source unit i = lane + 32 k sits at physical unit sync_phys_unit(lane) + 34 k (32 units = two regions of
+            // 17), and it is the first unit of a chunk exactly for lanes 4 and 20: the whole staging is 17 copies at
+            // constant offsets from two per-lane addresses, fully unrolled (the generic loop below spends ~28
+            // instructions per copy on the layout arithmetic).
+            static_assert(kSyncHaloSegs == 4 && kSyncChunkSegs == 16 && kSyncRegionUnits == 17, "staging offsets");
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + sync_phys_unit(lane));
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.units) + q0 + lane;
+            const bool first = lane == 4 || lane == 20;
+#pragma unroll
+            for (uint32_t k = 0; k < kSyncTileSrcUnits / 32; ++k) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 34u * 16u * k), "l"(src + 32u * k) : "memory");
+                if (first) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 34u * 16u * k - 16u), "l"(src + 32u * k) : "memory");
+            }
+            if (lane < kSyncTileSrcUnits % 32) {   // units 512..516: the look-ahead segment (+ the 4 units a repair may read)
+                const uint32_t k = kSyncTileSrcUnits / 32;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 34u * 16u * k), "l"(src + 32u * k) : "memory");
+                if (first) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 34u * 16u * k - 16u), "l"(src + 32u * k) : "memory");
+            }
+        } else {
 #pragma unroll 1
         for (uint32_t i = lane; i < kSyncTileSrcUnits; i += 32) {
             const int64_t q = q0 + i;
@@ -393,6 +413,7 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
             cp_async16_zfill(dst, src, bytes);
             // the first unit of a chunk also goes into the slot behind the previous region (or the tile halo)
             if (i >= kSyncHaloSegs && ((i - kSyncHaloSegs) & (kSyncChunkSegs - 1)) == 0) cp_async16_zfill(dst - 1, src, bytes);
+        }
         }
         cp_async_commit_wait_all();
         __syncwarp();
