@@ -409,7 +409,18 @@ HD_HD uint32_t sync_segment(uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, 
         const uint32_t s1 = sync_step<EXACT, LONG>(win, pos, L);
         const uint32_t p1 = pos + s1;
         const uint32_t s2 = sync_step<EXACT, LONG>(win << s1, p1, L);
+#if defined(__CUDA_ARCH__)
+        uint32_t np = p1;   // + s2 while still inside the segment: one predicated multiply-add (see sync_run)
+        asm("{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.lt.u32 p, %1, 128;\n\t"
+            "@p mad.lo.u32 %0, %2, %3, %0;\n\t"
+            "}"
+            : "+r"(np)
+            : "r"(p1), "r"(s2), "r"(L.one));
+#else
         const uint32_t np = p1 < kSegmentBits ? p1 + s2 : p1;
+#endif
         if ((np ^ pos) & 32u) {
             r0 = r1; r1 = r2; r2 = r3; r3 = r4;
 #if defined(__CUDA_ARCH__)

@@ -267,12 +267,12 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// loads the four units of (global) segment s from a warp's staged tile (layout: hd_internal.h) that starts at segment q0
-struct TileSegLoader {
-    const uint4 *tile;
-    int64_t q0;
+// loads segment s of the chunk that starts at segment seg0 from the owning lane's region of the staged tile
+struct RegionSegLoader {
+    const uint4 *region;
+    uint64_t seg0;
     __device__ __forceinline__ Seg4 operator()(uint64_t s) const {
-        const uint4 w = tile[sync_phys_unit((uint32_t)((int64_t)s - q0))];
+        const uint4 w = region[(uint32_t)(s - seg0)];
         Seg4 r;
         r.x = w.x; r.y = w.y; r.z = w.z; r.w = w.w;
         return r;
@@ -447,7 +447,9 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
         // redundancy 0.5) re-parses the head of its chunk from its left neighbour's landing, from the staged
         // tile; repeated until no lane changes (a parse that fails to merge inside a chunk moves on one lane per
         // round).  After this the tile is consistent given the entry of its FIRST owned chunk; check_seam() looks at that one.
-        const TileSegLoader tld{tile, q0};
+        // (a lane repairs its own chunk: segment seg0 + k is unit k of its region; k = 17 -- read ahead by
+        // sync_repair_chunk, never used -- falls on the next region's first unit)
+        const RegionSegLoader tld{tile + kSyncHaloSegs + 1 + kSyncRegionUnits * lane, chunk * kSyncChunkSegs};
         for (;;) {
             uint32_t left = __shfl_up_sync(0xffffffffu, words[1] >> 28, 1);
             if (p.use_tile_entry && lane == 1 && ticket > 0) left = p.tile_entry[ticket];   // exact (chased through the tile maps)
