@@ -66,6 +66,22 @@ struct TileParams {
 
 constexpr uint32_t kWarpRowBytes = 128;   // one row of a warp block: 32 lanes x 4 bytes
 
+// inclusive warp scan: the shuffle's own predicate (source lane in range) guards the add -- no lane comparisons
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 t;\n\t"
+            "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
+            "@p add.u32 %0, %0, t;\n\t"
+            "}"
+            : "+r"(v)
+            : "r"(d));
+    }
+    return v;
+}
 __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) {
     uint32_t r;
     asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
@@ -155,9 +171,9 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
             st_release_cta_u32(&s_t1_ready, 1u);
         }
         __syncwarp();
-        for (uint32_t k = 0;; ++k) {
+        for (uint32_t k = 0, k3 = 0;; ++k, k3 = k3 == 2u ? 0u : k3 + 1u) {   // k3 = k % 3
             const uint32_t b = k & 1u;
-            const uint64_t tile = s_tileid[k % 3u];
+            const uint64_t tile = s_tileid[k3];
             if (tile >= p.n_tiles) break;
             named_bar_sync(kBarFull + b, bar_threads);
             // ticket of step k+2.  Issued here, but no earlier: a tile must not be claimed long before it is decoded,
@@ -165,12 +181,7 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
             uint32_t ticket = 0;
             if (lane == 0) ticket = atomicAdd(p.tile_counter, 1u);
             const uint32_t wt = lane < nw ? s_wtot[b][lane] : 0u;
-            uint32_t wi = wt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
-                if (lane >= (uint32_t)d) wi += v;
-            }
+            const uint32_t wi = warp_incl_scan_u32(wt);
             if (lane < nw) s_wtot[b][lane] = wi - wt;   // exclusive warp offsets
             const uint64_t agg = __shfl_sync(0xffffffffu, wi, 31);
             // (the tile AGGREGATE was already published by the last decode warp to finish; tile 0 published its PREFIX)
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
                         p.shard_info[2] = gap_nibble(p.gap_words, p.n_segments - 1);   // where the parse leaves the shard
                     }
                 }
-                s_tileid[(k + 2u) % 3u] = ticket;   // slot (k+2)%3 held step k-1's tile, which nobody reads any more
+                s_tileid[k3 == 0u ? 2u : k3 - 1u] = ticket;   // slot (k+2)%3 held step k-1's tile, which nobody reads any more
             }
             __syncwarp();
             __threadfence_block();
@@ -296,9 +307,9 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
     };
     prefetch(s_tileid[0]);
 
-    for (uint32_t k = 0;; ++k) {
+    for (uint32_t k = 0, k3 = 0;; ++k, k3 = k3 == 2u ? 0u : k3 + 1u) {   // k3 = k % 3
         const uint32_t b = k & 1u;
-        const uint64_t tile = s_tileid[k % 3u];
+        const uint64_t tile = s_tileid[k3];
         const bool valid = tile < p.n_tiles;
         uint32_t cnt = 0, incl = 0;
         if (valid) {
@@ -326,12 +337,7 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
                                                   stage0_abs + b * stage_bytes + ((HD_WHATIF & 64) ? ((lane * 43u) & ~3u) : lane * 4u), nullptr);
             }
             // ---------------- warp-wide inclusive scan of the counts ----------------
-            incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= (uint32_t)d) incl += v;
-            }
+            incl = warp_incl_scan_u32(cnt);
             if (lane == 31) {
                 s_wtot[b][warp] = incl;
                 // the last warp to finish publishes the tile aggregate right away (tile 0: it is its own prefix)
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
         // the scan warp's prefix of tile k-1 (computed while this warp decoded tile k); its arrival also publishes the
         // ticket of step k+1 (k == 0: s_t1_ready above)
         if (prev_valid) mbar_wait_suspended(&s_ready[b ^ 1u], ((k - 1u) >> 1) & 1u);
-        if (valid) prefetch(s_tileid[(k + 1u) % 3u]);
+        if (valid) prefetch(s_tileid[k3 == 2u ? 0u : k3 + 1u]);
         if (prev_valid) {
             // ---------------- finish tile k-1: compact this warp's symbols in place and flush them ----------------
             const uint32_t pb = b ^ 1u;
