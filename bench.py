@@ -414,9 +414,11 @@ def ncu_traffic(mib, r, scheme):
         return None
 
 
-def roofline_of(algo_bytes, step_bytes, k4_ms, step_ms, kern, peak, peak_src, traffic=None):
+def roofline_of(algo_bytes, step_bytes, k4_ms, step_ms, kern, peak, peak_src, traffic=None, fixed=0):
     achieved = algo_bytes / (k4_ms * 1e-3) / 1e9 if k4_ms > 0 else 0.0
-    return {"bound": "hbm", "kernel": "hd_decode_tiles_kernel (K4 decode-and-write)", "achieved": round(achieved, 1),
+    kname = ("hd_decode_fixed_kernel<%d> (fixed-length code: every segment starts at a codeword boundary, no synchronisation, "
+             "no prescan, no gap words read)" % fixed) if fixed else "hd_decode_tiles_kernel (K4 decode-and-write)"
+    return {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1),
             "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
             "traffic": traffic,   # from the ncu capture of this workload under profiles/ (null: workload not captured)
             "algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": round(k4_ms, 4), "peak_source": peak_src,
@@ -452,12 +454,13 @@ def bench_selfsync_1gpu(hd, torch, T, data, units, lut, steps, warmup, clocks=No
     ms = T.run(step, dec.finish, steps, between=(clocks.sample if clocks else None))
     launches = hd.launch_count() - l0
     kern = T.kernels(hd, step, dec.finish, min(steps, 10))
+    fixed = table.fixed_length()
     table.close()
     n_seg = (len(units) + 3) // 4
-    algo = 4 * len(units) + n + 4 * ((n_seg + 7) // 8)      # K4 reads the gap words K1a left
     step_bytes = 4 * len(units) + n
+    algo = step_bytes if fixed else step_bytes + 4 * ((n_seg + 7) // 8)      # K4 reads the gap words K1a left
     return {"ms": sum(ms) / len(ms), "ms_median": float(np.median(ms)), "launches": launches, "kern": kern, "algo": algo,
-            "step_bytes": step_bytes, "parity": parity}
+            "step_bytes": step_bytes, "parity": parity, "fixed": fixed}
 
 
 def bench_gap_1gpu(hd, torch, T, data, pairs, units, gaps, steps, warmup):
@@ -476,10 +479,11 @@ def bench_gap_1gpu(hd, torch, T, data, pairs, units, gaps, steps, warmup):
         raise SystemExit("bench.py: gap-array decode differs from the original data -- not timing a wrong result")
     ms = T.run(step, None, steps)
     kern = T.kernels(hd, step, None, min(steps, 10))
+    fixed = table.fixed_length()
     table.close()
-    algo = 4 * len(units) + n + 4 * len(gaps)
+    algo = 4 * len(units) + n + (0 if fixed else 4 * len(gaps))   # (the fixed-length kernel does not read the gap array)
     return {"ms": sum(ms) / len(ms), "ms_median": float(np.median(ms)), "kern": kern, "algo": algo, "step_bytes": algo,
-            "parity": "byte-exact"}
+            "parity": "byte-exact", "fixed": fixed}
 
 
 def record(name, scheme, mib, r, res, n, peak, peak_src, input_desc, extra=None):
@@ -487,7 +491,7 @@ def record(name, scheme, mib, r, res, n, peak, peak_src, input_desc, extra=None)
     rec = {"config": name, "scheme": scheme, "mib": mib, "redundancy": r, "value": round(n / (ms * 1e-3) / 1e9, 2),
            "unit": "GB/s", "ms_per_step": round(ms, 4), "ms_per_step_mean": round(res["ms"], 4),
            "roofline": roofline_of(res["algo"], res["step_bytes"], res["kern"]["decode_write"], ms, res["kern"], peak, peak_src,
-                                   ncu_traffic(mib, r, scheme)),
+                                   ncu_traffic(mib, r, scheme), res.get("fixed", 0)),
            "parity": res["parity"], "input": input_desc}
     if extra:
         rec.update(extra)
@@ -545,7 +549,7 @@ def ours(args):
         ms_per_step = res["ms"]
         value = n / (ms_per_step * 1e-3) / 1e9
         roofline = roofline_of(res["algo"], res["step_bytes"], res["kern"]["decode_write"], ms_per_step, res["kern"], peak, peak_src,
-                               ncu_traffic(args.mib, r, "selfsync"))
+                               ncu_traffic(args.mib, r, "selfsync"), res.get("fixed", 0))
         launches, parity = res["launches"], res["parity"]
         n_total, n_units_total = n, len(units)
         input_desc = {"data": gen_src, "stream": enc_src}

@@ -42,7 +42,7 @@ _lib = None
 # every symbol include/hd_b200.h declares (tests check that all are exported)
 ABI_SYMBOLS = [
     "hd_version", "hd_status_string", "hd_last_cuda_error", "hd_warmup", "hd_table_from_flat_lut", "hd_table_from_lengths",
-    "hd_table_free", "hd_table_max_length", "hd_table_min_length", "hd_workspace_bytes_gap",
+    "hd_table_free", "hd_table_max_length", "hd_table_min_length", "hd_table_fixed_length", "hd_workspace_bytes_gap",
     "hd_workspace_bytes_selfsync", "hd_decode_gap", "hd_decode_selfsync", "hd_decode_gap_ex",
     "hd_decode_selfsync_ex", "hd_selfsync_gap_array", "hd_huff_parse", "hd_huff_image_bytes",
     "hd_huff_decode_host", "hd_build_code", "hd_flat_lut_from_lengths", "hd_encoded_size", "hd_encode",
@@ -87,6 +87,8 @@ def lib():
     L.hd_table_max_length.restype = u32
     L.hd_table_min_length.argtypes = [vp]
     L.hd_table_min_length.restype = u32
+    L.hd_table_fixed_length.argtypes = [vp]
+    L.hd_table_fixed_length.restype = u32
     L.hd_workspace_bytes_gap.argtypes = [u64]
     L.hd_workspace_bytes_gap.restype = sz
     L.hd_workspace_bytes_selfsync.argtypes = [u64]
@@ -326,6 +328,10 @@ class Codetable:
     @property
     def min_length(self):
         return lib().hd_table_min_length(self.handle)
+
+    def fixed_length(self):
+        """L if every codeword is L bits, L in {1, 2, 4, 8} (such streams take the dedicated kernel), else 0."""
+        return int(lib().hd_table_fixed_length(self.handle))
 
     def close(self):
         if self.handle:

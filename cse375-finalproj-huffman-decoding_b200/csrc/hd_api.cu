@@ -12,6 +12,7 @@
 #include <mutex>
 #include <new>
 
+#include "hd_fixed.cuh"
 #include "hd_kernels.cuh"
 #include "hd_decode.cuh"
 #include "hd_tables.cuh"
@@ -242,6 +243,58 @@ hd_status launch_tiles_geom(const TileGeom &g, const TileParams &p, cudaStream_t
     return HD_ERR_INVALID;
 }
 
+// ---- fixed-length codes (hd_fixed.cuh) ---------------------------------------------------------------------------
+// True if `t` is a complete code whose codewords all have the same length L in {1, 2, 4, 8}.
+bool fixed_length_code(const hd_table *t, uint32_t &L) {
+    const TableBlob &b = t->host;
+    L = b.min_len;
+    if (b.min_len != b.max_len || b.has_long) return false;   // (has_long also covers incomplete codes)
+    return L == 1 || L == 2 || L == 4 || L == 8;
+}
+
+bool g_fixed_fast_path = true;   // hd_set_tuning(-1, 0) switches it off (tests decode these codes through K1a + K4 too)
+
+template <int L>
+hd_status launch_fixed(const FixedParams &q, cudaStream_t s) {
+    const uint64_t total = q.n_segments * (128u / L);
+    const uint64_t blocks = std::max<uint64_t>(1, div_up(div_up(std::min(total, q.n_symbols), 16), 512));   // 16 output bytes per thread
+    const uint64_t cap = (uint64_t)device_info().sm_count * 4u;
+    hd_decode_fixed_kernel<L><<<(unsigned)std::min(blocks, cap), 512, 0, s>>>(q);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    HD_CUDA(cudaGetLastError());
+    return HD_OK;
+}
+
+hd_status run_fixed_decode(const uint32_t *d_units, uint64_t n_units, uint64_t n_segments, const hd_table *table, uint32_t L,
+                           uint8_t *d_out, uint64_t n_symbols, uint64_t *d_count, cudaStream_t s) {
+    FixedParams q;
+    q.units = d_units;
+    q.n_units = n_units;
+    q.n_segments = n_segments;
+    q.out = d_out;
+    q.n_symbols = n_symbols;
+    q.count_out = d_count;
+    // symbol of codeword c: first symbol of the primary LUT entry whose window starts with c
+    const uint32_t *dec = reinterpret_cast<const uint32_t *>(table->host.bytes.data());
+    const uint32_t lm = table->host.lut_bits;
+    std::memset(q.sym, 0, sizeof(q.sym));
+    for (uint32_t c = 0; c < (1u << L); ++c) q.sym[c] = (uint8_t)(dec[c << (lm - L)] >> 8);
+    ProfScope prof(HD_PROFILE_DECODE_WRITE, s);
+    switch (L) {
+        case 1: return launch_fixed<1>(q, s);
+        case 2: return launch_fixed<2>(q, s);
+        case 4: return launch_fixed<4>(q, s);
+        case 8: return launch_fixed<8>(q, s);
+    }
+    return HD_ERR_INVALID;
+}
+
+// The fast path applies to a whole stream that starts at bit 0 and writes to an aligned buffer; shards, chained pieces
+// and streams entered at an offset keep the general kernels.
+bool fixed_fast_ok(const hd_table *table, uint32_t first_bit, const uint8_t *d_out, uint32_t &L) {
+    return g_fixed_fast_path && first_bit == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0 && fixed_length_code(table, L);
+}
+
 hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32_t *d_gap_words,
                          uint64_t n_segments, uint32_t first_bit, const hd_table *table, uint8_t *d_out,
                          uint64_t n_symbols, const Workspace &w, uint64_t *d_count, cudaStream_t s,
@@ -249,6 +302,10 @@ hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32
                          uint64_t *shard_info = nullptr, bool already_zeroed = false,
                          const uint64_t *d_off_in = nullptr, uint64_t *d_off_out = nullptr,
                          const uint32_t *unconverged = nullptr) {
+    uint32_t fixed_len = 0;
+    if (!entry_word && !shard_info && !d_off_in && !d_off_out && !unconverged && fixed_fast_ok(table, first_bit, d_out, fixed_len))
+        return run_fixed_decode(d_units, n_units_readable > n_units ? n_units_readable : n_units, n_segments, table, fixed_len,
+                                d_out, n_symbols, d_count, s);
     TileGeom g;
     if (!pick_tile_geom(table, device_info().max_smem_optin, g)) return HD_ERR_INVALID;
     TileParams q;
@@ -652,6 +709,10 @@ hd_status hd_decode_selfsync_enqueue(const uint32_t *d_units, uint64_t n_units, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Workspace w = carve(d_workspace, n_units, true);
     const uint64_t n_seg = div_up(n_units, kSegmentUnits);
+    // a fixed-length code needs no synchronisation: every segment starts at a codeword boundary (hd_fixed.cuh)
+    uint32_t fixed_len = 0;
+    if (fixed_fast_ok(table, first_bit, d_out, fixed_len))
+        return run_fixed_decode(d_units, n_units, n_seg, table, fixed_len, d_out, n_symbols, d_count, s);
     // K1a + K1b, then K4 speculatively; the convergence flag is read once at the end (the reference reads a flag
     // array after every phase-2 launch, cuhd_gpu_decoder.cu:461-495).  One memset covers K4's ticket counter and
     // tile statuses and, right behind them, K1's control block.
@@ -1013,8 +1074,15 @@ int hd_mailbox_timed_out(hd_mailbox *m) {
 void hd_set_trace(void *) {}   // (the per-step trace of the round-1 kernel is gone; kept for ABI stability)
 void hd_set_tuning(int segs_per_thread, int threads_per_tile) {
     // warp-tile kernel: threads_per_tile = decode threads per CTA (a multiple of 32, at most 27 warps)
-    g_tile_segs = segs_per_thread;
+    // segs_per_thread < 0: also keep fixed-length codes on the general kernels (tests / A-B timing of hd_fixed.cuh)
+    g_fixed_fast_path = segs_per_thread >= 0;
+    g_tile_segs = segs_per_thread > 0 ? segs_per_thread : 0;
     g_tile_warps = (threads_per_tile > 0 && threads_per_tile % 32 == 0 && threads_per_tile <= (int)kTileMaxWarps * 32) ? threads_per_tile / 32 : 0;
+}
+
+uint32_t hd_table_fixed_length(const hd_table *table) {
+    uint32_t L = 0;
+    return (table && g_fixed_fast_path && fixed_length_code(table, L)) ? L : 0u;
 }
 
 // ---------------------------------------------------------------- profiling

@@ -313,8 +313,17 @@ hd_status hd_selfsync_decode_host(const uint32_t *units, uint64_t n_units,
 /* Tuning knob for benchmarks: 128-bit segments decoded per thread (1, 2 or 4)
  * and decode threads per CTA (a multiple of 32, at most 864 = 27 warps) of the
  * decode-and-write kernel; 0, 0 = automatic (two segments per thread when at
- * least 20 decode warps fit into the SM's shared memory, else one). */
+ * least 20 decode warps fit into the SM's shared memory, else one).
+ * segs_per_thread < 0 additionally keeps complete FIXED-LENGTH codes (every
+ * codeword L bits, L in {1, 2, 4, 8}) on the general kernels; by default a
+ * whole stream of such a code that starts at bit 0 and decodes into a 16-byte
+ * aligned buffer is decoded by one dedicated kernel (no synchronisation, no
+ * prescan: every segment starts at a codeword boundary and holds 128 / L
+ * symbols). */
 void hd_set_tuning(int segs_per_thread, int threads_per_tile);
+/* The codeword length L if `table` is such a fixed-length code (the dedicated kernel is used for whole streams from
+ * bit 0 into 16-byte aligned buffers), else 0. */
+uint32_t hd_table_fixed_length(const hd_table *table);
 /* Developer aid: device buffer (48 x 8 u64) that receives per-step %globaltimer
  * stamps of one CTA of the decode-and-write kernel; NULL switches it off. */
 void hd_set_trace(void *d_buf);

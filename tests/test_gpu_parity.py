@@ -191,6 +191,47 @@ def test_fixed_length_codes(hd, torch_cuda, length):
     assert np.array_equal(got2, data)
 
 
+@pytest.mark.parametrize("length", [1, 2, 4, 8])
+@pytest.mark.parametrize("n", [1, 17, 4095, 200003])
+def test_fixed_length_fast_path_equals_general_kernels(hd, torch_cuda, length, n):
+    """Codes whose codewords all have the same length L | 8 take the dedicated kernel (hd_fixed.cuh) when the stream
+    starts at bit 0 and the output is 16-byte aligned; hd_set_tuning(-1, 0) keeps them on K1a + K4.  Both must give the
+    original bytes, the same symbol count, and write nothing past the requested number of symbols."""
+    torch = torch_cuda
+    pairs = cases.fixed_length_code(1 << length, length)
+    data = cases.data_for_pairs(pairs, n, seed=100 + length)
+    units, gw, bits, lut = cases.oracle_stream(data, pairs, pad_unit=True)
+    d_units = hd.to_device_units(units)
+    d_units_gap = hd.to_device_units(units[:-1])
+    d_gaps = torch.from_numpy(np.ascontiguousarray(gw, dtype=np.uint32).view(np.int32)).cuda()
+    tab_ss = hd.Codetable(flat_lut=lut)
+    tab_gap = hd.Codetable(pairs=pairs)
+    dec_ss = hd.Decoder(d_units.numel(), selfsync=True)
+    dec_gap = hd.Decoder(d_units_gap.numel(), selfsync=False)
+    try:
+        for fast in (True, False):
+            hd.set_tuning(0 if fast else -1, 0)
+            launches = hd.launch_count()
+            for want_n in sorted({n, max(1, n - 1), max(1, n // 2)}):
+                for shift in (0, 3):   # an unaligned output always takes the general kernels
+                    buf = torch.full((n + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+                    dec_ss.decode_selfsync(d_units, tab_ss, want_n, out=buf[shift:shift + want_n])
+                    res = buf.cpu().numpy()
+                    assert np.array_equal(res[shift:shift + want_n], data[:want_n]), ("selfsync", fast, want_n, shift)
+                    assert (res[:shift] == 0xEE).all() and (res[shift + want_n:] == 0xEE).all()
+                    assert int(dec_ss.count.item()) == want_n
+                    buf.fill_(0xEE)
+                    dec_gap.decode_gap(d_units_gap, d_gaps, tab_gap, want_n, out=buf[shift:shift + want_n])
+                    res = buf.cpu().numpy()
+                    assert np.array_equal(res[shift:shift + want_n], data[:want_n]), ("gap", fast, want_n, shift)
+                    assert (res[:shift] == 0xEE).all() and (res[shift + want_n:] == 0xEE).all()
+            del launches
+    finally:
+        hd.set_tuning(0, 0)
+        tab_ss.close()
+        tab_gap.close()
+
+
 def test_long_codes_up_to_16_bits(hd, torch_cuda):
     pairs = cases.skewed_long_code()
     for geometric in (True, False):
