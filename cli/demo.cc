@@ -6,6 +6,8 @@
 #include <cuhd.h>
 #include <llhuff.h>
 
+#include <chrono>
+#include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <vector>
@@ -68,17 +70,31 @@ int main(int argc, char **argv) {
     auto gpu_table = std::make_shared<cuhd::CUHDGPUCodetable>(dec_table);
     auto gpu_aux = std::make_shared<cuhd::CUHDGPUDecoderMemory>(in_buf->get_compressed_size_units(), SUBSEQ_SIZE,
                                                                 NUM_THREADS);
+    // HD_DEMO_VERBOSE=1: where the "Decompression time" goes (stderr; the reference times the same region as a whole)
+    const bool verbose = std::getenv("HD_DEMO_VERBOSE") != nullptr;
+    auto lap = [&, t = std::chrono::steady_clock::now()](const char *what) mutable {
+        if (!verbose) return;
+        const auto n = std::chrono::steady_clock::now();
+        std::cerr << "  " << what << ": " << std::chrono::duration<double, std::milli>(n - t).count() << " ms" << std::endl;
+        t = n;
+    };
+    lap("(start)");
     TIMER_START(timings, "Decompression time")
         gpu_in->allocate();
         gpu_out->allocate();
         gpu_table->allocate();
         gpu_aux->allocate();
+        lap("4 x allocate (cudaMalloc)");
         gpu_table->cpy_host_to_device();
+        lap("table upload");
         gpu_in->cpy_host_to_device();
+        lap("stream H2D");
         cuhd::CUHDGPUDecoder::decode(gpu_in, in_buf->get_compressed_size_units(), gpu_out,
                                      out_buf->get_uncompressed_size(), gpu_table, gpu_aux, MAX_CODEWORD_LENGTH,
                                      SUBSEQ_SIZE, NUM_THREADS);
+        lap("decode");
         gpu_out->cpy_device_to_host();
+        lap("output D2H");
     TIMER_STOP
 
     for (auto &t : timings) std::cout << t.first << ".. " << t.second << "µs" << std::endl;

@@ -481,6 +481,14 @@ hd_status finish_sync(const SyncLaunch &L, cudaStream_t s, bool *extra_rounds) {
     return HD_OK;
 }
 
+// the pinned word a synchronous self-sync decode reads its convergence flag into: one per host thread, made once
+// (hd_warmup makes it ahead of the first decode)
+uint32_t *thread_flag() {
+    static thread_local uint32_t *h_flag = nullptr;
+    if (!h_flag && cudaHostAlloc(reinterpret_cast<void **>(&h_flag), 64, cudaHostAllocDefault) != cudaSuccess) h_flag = nullptr;
+    return h_flag;
+}
+
 }  // namespace
 
 extern "C" {
@@ -505,6 +513,8 @@ const char *hd_last_cuda_error(void) { return cudaGetErrorString(g_last_cuda); }
 // its first launch: tens of milliseconds that would otherwise land inside the first timed decode of a process).
 hd_status hd_warmup(void) {
     HD_CUDA(cudaFree(nullptr));
+    (void)device_info();
+    if (!thread_flag()) { g_last_cuda = cudaGetLastError(); return HD_ERR_CUDA; }   // (a pinned allocation costs milliseconds)
     cudaFuncAttributes a;
 #define HD_TOUCH(k) HD_CUDA(cudaFuncGetAttributes(&a, k))
 #define HD_TOUCH_TILES(L)                                                                                  \
@@ -517,6 +527,8 @@ hd_status hd_warmup(void) {
     HD_TOUCH((hd_sync_parse_kernel<true, false>)); HD_TOUCH((hd_sync_parse_kernel<true, true>));
     HD_TOUCH((hd_sync_walk_kernel<false, false>)); HD_TOUCH((hd_sync_walk_kernel<false, true>));
     HD_TOUCH((hd_sync_walk_kernel<true, false>)); HD_TOUCH((hd_sync_walk_kernel<true, true>));
+    HD_TOUCH((hd_decode_fixed_kernel<1>)); HD_TOUCH((hd_decode_fixed_kernel<2>));
+    HD_TOUCH((hd_decode_fixed_kernel<4>)); HD_TOUCH((hd_decode_fixed_kernel<8>));
 #undef HD_TOUCH_TILES
 #undef HD_TOUCH
     (void)a;
@@ -754,8 +766,8 @@ hd_status hd_decode_selfsync_finish(const uint32_t *d_units, uint64_t n_units, u
 hd_status hd_decode_selfsync_ex(const uint32_t *d_units, uint64_t n_units, uint32_t first_bit,
                                 const hd_table *table, uint8_t *d_out, uint64_t n_symbols, void *d_workspace,
                                 size_t workspace_bytes, uint64_t *d_count, void *stream) {
-    static thread_local uint32_t *h_flag = nullptr;   // pinned, one per host thread
-    if (!h_flag) HD_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&h_flag), 64, cudaHostAllocDefault));
+    uint32_t *h_flag = thread_flag();   // pinned, one per host thread
+    if (!h_flag) { g_last_cuda = cudaGetLastError(); return HD_ERR_CUDA; }
     hd_status st = hd_decode_selfsync_enqueue(d_units, n_units, first_bit, table, d_out, n_symbols, d_workspace,
                                               workspace_bytes, d_count, h_flag, stream);
     if (st != HD_OK) return st;

@@ -12,8 +12,10 @@ for r in 0.5 0.9; do
   (cd $W && $R/oracle/_ref/generate 104857600 $r > /dev/null && mv data.bin data100_100.bin && cp data100_100.bin input_data.bin)
   echo "=== redundancy $r: reference gpuhd demo (self-sync; 'Decompression time' = malloc + H2D + decode + D2H) ==="
   (cd $W/run && timeout 300 $R/oracle/_ref/gpuhd_demo 0 100) 2>&1 | tail -7
-  echo "=== redundancy $r: our bin/demo on the same file (2nd line: a second process) ==="
-  (cd $W/run && timeout 300 $B/demo 0 100 | grep -E "Decompression|mismatch"; timeout 300 $B/demo 0 100 | grep -E "Decompression|mismatch")
+  echo "--- four more processes of the reference demo (the timed region holds four cudaMalloc calls: single runs vary by tens of ms) ---"
+  (cd $W/run && for i in 1 2 3 4; do timeout 300 $R/oracle/_ref/gpuhd_demo 0 100 2>&1 | grep -E "Decompression time|mismatch" | tr '\n' ' '; echo; done)
+  echo "=== redundancy $r: our bin/demo on the same file (five processes) ==="
+  (cd $W/run && for i in 1 2 3 4 5; do timeout 300 $B/demo 0 100 | grep -E "Decompression time|mismatch" | tr '\n' ' '; echo; done)
   echo "=== redundancy $r: reference gap-array encoder + decoder ('dec,' = kernel ms, mean of 100 runs) ==="
   (cd $W && timeout 300 $R/oracle/_ref/gap_encoder data100_100.bin ref.huff 2>&1 | tail -4; timeout 600 $R/oracle/_ref/gap_decoder ref.huff decoded_ref 2>&1 | tail -5; cmp decodedfile data100_100.bin && echo "reference decoder output: identical" || echo "reference decoder output: DIFFERS")
   echo "=== redundancy $r: our bin/decoder on the reference's .huff ==="
