@@ -56,9 +56,11 @@ const char *hd_version(void);
 const char *hd_status_string(hd_status s);
 /* last cudaError_t seen by this library on the calling thread, as text */
 const char *hd_last_cuda_error(void);
-/* optional: create the CUDA context of the current device and load the decode
- * kernels now (CUDA loads kernel code lazily at the first launch; the reference
- * demos time their first and only decode, gpuhd/src/demo.cc:170-197) */
+/* optional: create the CUDA context of the current device, load the decode
+ * kernels and make the calling thread's pinned convergence flag now (CUDA loads
+ * kernel code lazily at the first launch and a pinned allocation costs
+ * milliseconds; the reference demos time their first and only decode,
+ * gpuhd/src/demo.cc:170-197).  Call it on the thread that will decode. */
 hd_status hd_warmup(void);
 
 /* ------------------------------------------------------------------ tables
