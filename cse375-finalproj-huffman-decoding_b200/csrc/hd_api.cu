@@ -218,11 +218,29 @@ bool pick_tile_geom(const hd_table *t, int max_smem, TileGeom &g) {
 }
 
 template <int SEGS, int RCAP, bool LONG>
-hd_status launch_tiles(const TileParams &p, size_t smem, cudaStream_t s) {
+hd_status launch_tiles(const TileParams &p, size_t smem, cudaStream_t s, bool after_sync) {
     auto kern = hd_decode_tiles_kernel<SEGS, RCAP, LONG>;
     HD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint64_t grid = (uint64_t)device_info().sm_count;   // persistent: one CTA per SM, all co-resident (the look-back spins)
     if (grid > p.n_tiles) grid = p.n_tiles;
+    if (after_sync && !(HD_WHATIF & 16384)) {
+        // K4 right behind K1a on the stream: programmatic dependent launch.  K1a triggers at its start, so a K4 CTA is
+        // placed on an SM as soon as that SM's K1a CTA has exited; it stages its tables and takes its first ticket while
+        // the last K1a warps finish, and waits (cudaGridDependencySynchronize) before it reads the gap words.
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((p.n_warps + 1) * 32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        HD_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return HD_OK;
+    }
     kern<<<(unsigned)grid, (p.n_warps + 1) * 32, smem, s>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     HD_CUDA(cudaGetLastError());
@@ -230,15 +248,15 @@ hd_status launch_tiles(const TileParams &p, size_t smem, cudaStream_t s) {
 }
 
 template <bool LONG>
-hd_status launch_tiles_geom(const TileGeom &g, const TileParams &p, cudaStream_t s) {
+hd_status launch_tiles_geom(const TileGeom &g, const TileParams &p, cudaStream_t s, bool after_sync) {
     switch (g.segs * 100 + g.rcap) {
-        case 112: return launch_tiles<1, 12, LONG>(p, g.smem, s);
-        case 124: return launch_tiles<1, 24, LONG>(p, g.smem, s);
-        case 136: return launch_tiles<1, 36, LONG>(p, g.smem, s);
-        case 212: return launch_tiles<2, 12, LONG>(p, g.smem, s);
-        case 224: return launch_tiles<2, 24, LONG>(p, g.smem, s);
-        case 236: return launch_tiles<2, 36, LONG>(p, g.smem, s);
-        case 424: return launch_tiles<4, 24, LONG>(p, g.smem, s);
+        case 112: return launch_tiles<1, 12, LONG>(p, g.smem, s, after_sync);
+        case 124: return launch_tiles<1, 24, LONG>(p, g.smem, s, after_sync);
+        case 136: return launch_tiles<1, 36, LONG>(p, g.smem, s, after_sync);
+        case 212: return launch_tiles<2, 12, LONG>(p, g.smem, s, after_sync);
+        case 224: return launch_tiles<2, 24, LONG>(p, g.smem, s, after_sync);
+        case 236: return launch_tiles<2, 36, LONG>(p, g.smem, s, after_sync);
+        case 424: return launch_tiles<4, 24, LONG>(p, g.smem, s, after_sync);
     }
     return HD_ERR_INVALID;
 }
@@ -301,7 +319,7 @@ hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32
                          uint64_t n_units_readable = 0, const uint32_t *entry_word = nullptr,
                          uint64_t *shard_info = nullptr, bool already_zeroed = false,
                          const uint64_t *d_off_in = nullptr, uint64_t *d_off_out = nullptr,
-                         const uint32_t *unconverged = nullptr) {
+                         const uint32_t *unconverged = nullptr, bool after_sync = false) {
     uint32_t fixed_len = 0;
     if (!entry_word && !shard_info && !d_off_in && !d_off_out && !unconverged && fixed_fast_ok(table, first_bit, d_out, fixed_len))
         return run_fixed_decode(d_units, n_units_readable > n_units ? n_units_readable : n_units, n_segments, table, fixed_len,
@@ -334,7 +352,7 @@ hd_status run_gap_decode(const uint32_t *d_units, uint64_t n_units, const uint32
     q.k_pair_slope = kPairSelSlope;
     if (!already_zeroed) HD_CUDA(cudaMemsetAsync(w.tile_counter, 0, w.zero_bytes, s));
     ProfScope prof(HD_PROFILE_DECODE_WRITE, s);
-    return table->host.has_long ? launch_tiles_geom<true>(g, q, s) : launch_tiles_geom<false>(g, q, s);
+    return table->host.has_long ? launch_tiles_geom<true>(g, q, s, after_sync) : launch_tiles_geom<false>(g, q, s, after_sync);
 }
 
 hd_status check_common(const uint32_t *d_units, uint64_t n_units, const hd_table *table, const uint8_t *d_out,
@@ -733,7 +751,7 @@ hd_status hd_decode_selfsync_enqueue(const uint32_t *d_units, uint64_t n_units, 
     st = run_sync(L, s);
     if (st != HD_OK) return st;
     st = run_gap_decode(d_units, n_units, w.gap_words, n_seg, first_bit, table, d_out, n_symbols, w, d_count, s, 0, nullptr,
-                        nullptr, true);
+                        nullptr, true, nullptr, nullptr, nullptr, true);
     if (st != HD_OK) return st;
     if (L.p.n_chunks > 1) HD_CUDA(cudaMemcpyAsync(h_unconverged, w.changed, 4, cudaMemcpyDeviceToHost, s));
     return HD_OK;

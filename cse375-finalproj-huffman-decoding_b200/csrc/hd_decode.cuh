@@ -161,6 +161,9 @@ __global__ void __launch_bounds__(896, 1) hd_decode_tiles_kernel(const TileParam
         }
     }
     __syncthreads();
+    // launched right behind the synchronisation kernel (programmatic dependent launch): everything above overlapped its
+    // tail; its gap words are read from here on.  (Returns at once for an ordinary launch.)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t bar_threads = nthreads;
 
     if (warp == nw) {

@@ -317,6 +317,9 @@ __global__ void __launch_bounds__(kSyncWarps * 32, 1) hd_sync_parse_kernel(const
     }
     L.one = p.k_one;
     __syncthreads();
+    // the decode kernel may be launched as a programmatic dependent of this one: let its CTAs be placed as soon as SMs
+    // free up (they wait for this grid to complete before they read the gap words)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 *tile = reinterpret_cast<uint4 *>(smem + tiles_off + (size_t)warp * kSyncTileBytes);
     const uint32_t land_abs = (uint32_t)__cvta_generic_to_shared(tile + kSyncTilePhysUnits);   // landing bytes [slot][lane]
